@@ -1,0 +1,145 @@
+/* phiseg_sm100.h -- C-ABI of libphiseg_sm100.so: hand-written sm_100a CUDA kernels for the PHiSeg hot path.
+ *
+ * The reference (baumgach/PHiSeg-code) has no FFI: its op layer is TensorFlow-1.12 library calls made from
+ * tfwrapper/layers.py, tfwrapper/normalisation.py and phiseg/phiseg_model.py.  Each entry point below names the
+ * reference call site (file:line under /root/reference) whose device work it replaces.  Conventions:
+ *   - every tensor is NHWC, described by phs_tensor {ptr,N,H,W,C,ld,dtype}; ld = pixel pitch in ELEMENTS
+ *     (ld >= C lets a tensor be a channel slice of a wider buffer: zero-copy tf.concat);
+ *   - dtype 0 = float32, 1 = bfloat16; filters are HWIO float32 masters (tfwrapper/layers.py:115) plus bf16
+ *     shadows in the two K-major layouts the tensor-core kernels read (see phs_weight_prep);
+ *   - the caller owns all memory (device pointers, e.g. torch tensors' data_ptr()); nothing is allocated,
+ *     no implicit synchronisation, all work is enqueued on `stream` (a cudaStream_t);
+ *   - return value 0 = ok, <0 = argument error, >0 = cudaError_t; phs_last_error() gives the message.
+ */
+#ifndef PHISEG_SM100_H
+#define PHISEG_SM100_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHS_F32 0
+#define PHS_BF16 1
+
+#define PHS_NORM_BN_TRAIN 0 /* tfwrapper/normalisation.py:145-163, is_training=True  */
+#define PHS_NORM_BN_INFER 1 /* same, is_training=False (moving statistics)            */
+#define PHS_NORM_GN 2       /* tfwrapper/normalisation.py:17-36                       */
+
+#define PHS_IMPL_SIMT 0 /* fp32-accumulate CUDA-core kernels (parity mode, odd shapes)            */
+#define PHS_IMPL_TC 1   /* tcgen05 implicit GEMM, TMA-staged, TMEM accumulators (bf16 operands)  */
+
+typedef struct {
+  void* ptr;
+  int32_t N, H, W, C;
+  int32_t ld;    /* pixel pitch in elements */
+  int32_t dtype; /* PHS_F32 | PHS_BF16 */
+} phs_tensor;
+
+int phs_version(void);
+int phs_arch(void); /* 100: built for sm_100a */
+const char* phs_last_error(void);
+/* 1 if the current device can run the tcgen05 kernels (compute capability 10.x), else 0 */
+int phs_device_ok(void);
+
+/* ---- convolution: tf.nn.conv2d(x, W, [1,1,1,1], "SAME") + tf.nn.bias_add (tfwrapper/layers.py:123,132) ------
+ * ksize in {1,3}.  dgrad != 0 computes the input gradient instead (dx = conv(dy, rot180(W)^T)), i.e. the
+ * Conv2DBackpropInput that optimizer.minimize (phiseg/phiseg_model.py:141) adds.  accumulate != 0: y += result.
+ * SIMT: w = float32 HWIO master.  TC: w = bf16 shadow from phs_weight_prep (fwd layout, or dgrad layout when dgrad). */
+int phs_conv2d(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
+               int accumulate, int impl, void* stream);
+/* forward convolution (tensor-core path only) that also accumulates, from the fp32 accumulators, the per-(sample,
+ * channel) sum and sum of squares the following batch_norm / group_norm2D needs: stats[N][C][2] must be zeroed. */
+int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
+                     float* stats, void* stream);
+/* Conv2DBackpropFilter: dw[kh][kw][ci][co] (+)= sum x[.,h+kh-p,w+kw-p,ci]*dy[.,h,w,co]; db (+)= sum dy (may be NULL).
+ * dw/db are float32 in the HWIO master layout.  The TC variant accumulates with atomics: zero or reuse dw first. */
+int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,
+                     int impl, void* stream);
+
+/* ---- normalisation + activation -------------------------------------------------------------------------- */
+/* per-(sample,channel) sum and sum of squares of y: stats[N][C][2] (overwritten). */
+int phs_chan_stats(const phs_tensor* y, float* stats, void* stream);
+/* stats -> mean[N][C], rstd[N][C] for batch_norm (train: batch statistics + moving-average update with decay,
+ * Bessel-corrected variance; infer: moving statistics) or group_norm2D (groups of C/max(2,C/16) channels). */
+int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
+                      float* moving_var, float* mean, float* rstd, void* stream);
+/* a = act(gamma*(y-mean)*rstd + beta); relu != 0 applies tf.nn.relu (tfwrapper/layers.py:134-135). */
+int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     int relu, const phs_tensor* a, void* stream);
+/* backward of the above, three launches: sums[N][C][2] = (sum g*mask, sum g*mask*xhat) ... */
+int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, int relu, float* sums, void* stream);
+/* ... dgamma/dbeta (+= when accumulate) and per-(n,c) coefficients coef[N][C][2]; dbias (may be NULL) is the
+ * gradient of the conv bias that precedes the norm, derived analytically from the forward statistics ... */
+int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* mean, const float* rstd,
+                          const float* gamma, int N, int HW, int C, int mode, float* coef, float* dgamma, float* dbeta,
+                          float* dbias, int accumulate, void* stream);
+/* ... dy = rstd*(g*mask*gamma - m1 - xhat*m2). */
+int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, const float* coef, const phs_tensor* dy,
+                       void* stream);
+
+/* ---- resampling ------------------------------------------------------------------------------------------ */
+/* tf.nn.avg_pool 2x2/2 (tfwrapper/layers.py:44-54) and its adjoint */
+int phs_avgpool2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream);
+int phs_avgpool2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate, void* stream);
+/* TF1 legacy bilinear x2, align_corners=False (tfwrapper/layers.py:336-345) and its adjoint */
+int phs_upsample2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream);
+int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate, void* stream);
+
+/* ---- latent heads: softplus, reparameterisation, KL (posteriors.py:105-108,125-128; phiseg_model.py:210-226) */
+/* All tensors float32 [N, hw, zd] flattened (count = N*hw*zd; per_sample = hw*zd).  sp_* are pre-softplus sigma
+ * maps.  gap != 0: ProbUNet form, mu/sigma are means over the hw positions (posteriors.py:41-45) and outputs are [N,zd].
+ * z = mu_q + sigma_q*eps (use_prior_z: z = mu_p + sigma_p*eps, priors.py:100).  kl_out (may be NULL) += kl_scale * sum KL. */
+int phs_latent_fwd(const float* mu_q, const float* sp_q, const float* mu_p, const float* sp_p, const float* eps, int N,
+                   int hw, int zd, int gap, int use_prior_z, float* mu_q_out, float* sigma_q, float* mu_p_out,
+                   float* sigma_p, float* z, float* kl_out, float kl_scale, void* stream);
+/* gradients wrt the four head maps given dz and the KL weight (kl_scale = KL_w * 4^l / B). */
+int phs_latent_bwd(const float* dz, const float* mu_q, const float* sp_q, const float* sigma_q, const float* mu_p,
+                   const float* sp_p, const float* sigma_p, const float* eps, int N, int hw, int zd, int gap,
+                   float kl_scale, float* d_mu_q, float* d_sp_q, float* d_mu_p, float* d_sp_p, void* stream);
+
+/* ---- multi-scale residual cross-entropy (phiseg_model.py:229-262, likelihoods.py:218-221) ------------------ */
+/* logits[l]: float32 [N, H>>l, W>>l, nlabels] native-resolution head outputs, l = 0..L-1; labels uint8 [N,H,W].
+ * loss_out[l] += scale * sum over pixels of xent(onehot, s_accum[l]) with s_accum[l] = sum_{i>=l} NN-upsample(logits[i]).
+ * dlogits[l] (may be NULL => forward only) receive d(sum_l loss_l)/d logits[l] (buffers must be zeroed by the caller). */
+int phs_xent_multiscale(const float* const* logits, float* const* dlogits, const uint8_t* labels, int N, int H, int W,
+                        int nlabels, int L, float scale, float* loss_out, void* stream);
+/* s_out = sum_l NN-upsample(logits[l]) (phiseg_model.py:304-311); optional softmax / running sum / argmax outputs. */
+int phs_aggregate_logits(const float* const* logits, int N, int H, int W, int nlabels, int L, float* s_out,
+                         float* softmax_out, float* softmax_accum, int64_t* argmax_out, void* stream);
+
+/* ---- optimizer (phiseg_model.py:134-141): tf.train.AdamOptimizer, TF "epsilon-hat" form -------------------- */
+/* lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); when lr_t_dev != NULL the step size is read from device memory instead
+ * (lets a captured CUDA graph of the whole training step be replayed with a new learning rate). */
+int phs_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, const float* lr_t_dev,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* tf.train.MomentumOptimizer(momentum, use_nesterov=True) */
+int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr, const float* lr_dev, float momentum,
+                      float grad_scale, void* stream);
+/* bf16 shadows of every conv filter for the tensor-core kernels.  table: int64[nconv][6] =
+ * {src_off (floats into master), fwd_off, dgrad_off (bf16 elements into shadow), taps, cin, cout}.
+ * fwd layout  [cout][tap*cin + ci]; dgrad layout [cin][(taps-1-tap)*cout + co]. */
+int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream);
+
+/* ---- small helpers --------------------------------------------------------------------------------------- */
+/* dst[.., c_off + c] = src[.., c] with dtype conversion (strided channel-slice copy) */
+int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream);
+/* posterior input tf.concat([x, one_hot(s) - 0.5], -1) (phiseg_model.py:29, posteriors.py:87) */
+int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, int Cx, int nlabels,
+                        const phs_tensor* out, void* stream);
+/* ProbUNet: tile z [N,zd] over H x W into a channel slice (likelihoods.py:147-151) and the adjoint reduction */
+int phs_broadcast_z(const float* z, const phs_tensor* out, void* stream);
+int phs_broadcast_z_bwd(const phs_tensor* g, float* dz, int accumulate, void* stream);
+int phs_fill_f32(float* p, int64_t n, float v, void* stream);
+/* dst (+)= src over float buffers */
+int phs_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream);
+/* out[0] += scale * sum(src^2): the tf.nn.l2_loss terms of add_weight_decay (phiseg_model.py:290-300) */
+int phs_sumsq_f32(const float* src, int64_t n, float scale, float* out, void* stream);
+/* first-maximum argmax over the label axis of [npix, nlabels] (np.argmax in predict, phiseg_model.py:351-353) */
+int phs_argmax_f32(const float* src, int64_t npix, int nlabels, int64_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

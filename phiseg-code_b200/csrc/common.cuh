@@ -1,0 +1,114 @@
+// Shared device/host helpers for libphiseg_sm100.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/phiseg_sm100.h"
+
+typedef __nv_bfloat16 bf16;
+
+void phs_set_error(const char* fmt, ...);
+int phs_check_launch(const char* what);
+
+#define PHS_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      phs_set_error(__VA_ARGS__);     \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- dtype-generic scalar/vector access ------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// V consecutive channels; V==8 => one 16-byte access for bf16, two for float; V==4 likewise; V==1 scalar
+template <typename T, int V>
+__device__ __forceinline__ void ldv(const T* p, float* out) {
+  if constexpr (V == 1) {
+    out[0] = ldf<T>(p);
+  } else if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+      out[i] = t.x; out[i + 1] = t.y; out[i + 2] = t.z; out[i + 3] = t.w;
+    }
+  } else {
+    static_assert(V == 8 || V == 4, "bf16 vector width");
+    if constexpr (V == 8) {
+      uint4 t = *reinterpret_cast<const uint4*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        out[2 * i] = f.x; out[2 * i + 1] = f.y;
+      }
+    } else {
+      uint2 t = *reinterpret_cast<const uint2*>(p);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        out[2 * i] = f.x; out[2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void stv(T* p, const float* in) {
+  if constexpr (V == 1) {
+    stf<T>(p, in[0]);
+  } else if constexpr (sizeof(T) == 4) {
+#pragma unroll
+    for (int i = 0; i < V; i += 4)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(in[i], in[i + 1], in[i + 2], in[i + 3]);
+  } else {
+    if constexpr (V == 8) {
+      uint4 t;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+      *reinterpret_cast<uint4*>(p) = t;
+    } else {
+      uint2 t;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+      *reinterpret_cast<uint2*>(p) = t;
+    }
+  }
+}
+
+// widest vector (in elements) usable for a channel-slice tensor
+static inline int pick_vec(const phs_tensor* t) {
+  int es = t->dtype == PHS_BF16 ? 2 : 4;
+  uintptr_t a = (uintptr_t)t->ptr;
+  if (t->C % 8 == 0 && t->ld % 8 == 0 && a % (8 * es > 16 ? 16 : 8 * es) == 0) return 8;
+  if (t->C % 4 == 0 && t->ld % 4 == 0 && a % (4 * es > 16 ? 16 : 4 * es) == 0) return 4;
+  return 1;
+}
+static inline int min_vec(int a, int b) { return a < b ? a : b; }
+
+#define PHS_DISPATCH_DTYPE(dt, T, ...)                  \
+  if ((dt) == PHS_F32) { typedef float T; __VA_ARGS__; } \
+  else { typedef bf16 T; __VA_ARGS__; }
+
+#define PHS_DISPATCH_VEC(v, V, ...)                        \
+  if ((v) == 8) { constexpr int V = 8; __VA_ARGS__; }        \
+  else if ((v) == 4) { constexpr int V = 4; __VA_ARGS__; }   \
+  else { constexpr int V = 1; __VA_ARGS__; }

@@ -1,0 +1,719 @@
+// Memory-bound kernels of the PHiSeg hot path: normalisation (batch_norm / group_norm2D) forward and backward,
+// 2x2 average pool, TF1-legacy bilinear x2 up-sampling, their adjoints, and small helpers.
+// All tensors NHWC with a pixel pitch (ld) so that channel slices of concat buffers are addressed in place.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// per-(sample, channel) reductions.  grid = (chunks, N); each block walks a contiguous run of pixels of one
+// sample with CW channel-vector lanes x PL pixel lanes, reduces the pixel lanes through shared memory and
+// issues one atomicAdd per (n, c, quantity).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+
+template <typename T, int V>
+__global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __restrict__ y, int HW, int C, int ld,
+                                                                 int pix_per_block, float* __restrict__ stats) {
+  const int n = blockIdx.y;
+  const int nvec = C / V;
+  const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
+  const int PL = RED_THREADS / CW;
+  const int lane_c = threadIdx.x % CW, lane_p = threadIdx.x / CW;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  extern __shared__ float sm[];  // [PL][C][2]
+  const T* base = y + (size_t)n * HW * ld;
+  for (int cv = lane_c; cv < nvec; cv += CW) {
+    float s[V], q[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+    if (lane_p < PL) {
+      for (int p = p0 + lane_p; p < p1; p += PL) {
+        float v[V];
+        ldv<T, V>(base + (size_t)p * ld + cv * V, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+      }
+      float* d = sm + ((size_t)lane_p * C + cv * V) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { d[2 * i] = s[i]; d[2 * i + 1] = q[i]; }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += RED_THREADS) {
+    float a = 0.f;
+    for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
+    atomicAdd(&stats[(size_t)n * C * 2 + i], a);
+  }
+}
+
+// sums[n][c] = (sum g*mask, sum g*mask*xhat)
+template <typename T, int V>
+__global__ void __launch_bounds__(RED_THREADS)
+    norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
+                           int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                           float* __restrict__ sums) {
+  const int n = blockIdx.y;
+  const int nvec = C / V;
+  const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
+  const int PL = RED_THREADS / CW;
+  const int lane_c = threadIdx.x % CW, lane_p = threadIdx.x / CW;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  extern __shared__ float sm[];
+  const T* gb = g + (size_t)n * HW * ldg;
+  const T* yb = y + (size_t)n * HW * ldy;
+  for (int cv = lane_c; cv < nvec; cv += CW) {
+    float s1[V], s2[V], mu[V], rs[V], ga[V], be[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      int c = cv * V + i;
+      s1[i] = s2[i] = 0.f;
+      mu[i] = mean[(size_t)n * C + c];
+      rs[i] = rstd[(size_t)n * C + c];
+      ga[i] = gamma[c];
+      be[i] = beta[c];
+    }
+    if (lane_p < PL) {
+      for (int p = p0 + lane_p; p < p1; p += PL) {
+        float gv[V], yv[V];
+        ldv<T, V>(gb + (size_t)p * ldg + cv * V, gv);
+        ldv<T, V>(yb + (size_t)p * ldy + cv * V, yv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float xh = (yv[i] - mu[i]) * rs[i];
+          float a = ga[i] * xh + be[i];
+          float gm = (relu && a <= 0.f) ? 0.f : gv[i];
+          s1[i] += gm;
+          s2[i] += gm * xh;
+        }
+      }
+      float* d = sm + ((size_t)lane_p * C + cv * V) * 2;
+#pragma unroll
+      for (int i = 0; i < V; ++i) { d[2 * i] = s1[i]; d[2 * i + 1] = s2[i]; }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += RED_THREADS) {
+    float a = 0.f;
+    for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
+    atomicAdd(&sums[(size_t)n * C * 2 + i], a);
+  }
+}
+
+static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size_t* smem) {
+  int nvec = C / V;
+  int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
+  int PL = RED_THREADS / CW;
+  // aim at >= ~4 blocks per SM overall while keeping >= 64 pixels per pixel-lane where possible
+  int target_blocks = 148 * 4;
+  int chunks = (target_blocks + N - 1) / N;
+  int max_chunks = (HW + PL * 8 - 1) / (PL * 8);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  *ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + *ppb - 1) / *ppb;
+  *grid = dim3(chunks, N);
+  *smem = (size_t)PL * C * 2 * sizeof(float);
+}
+
+int phs_chan_stats(const phs_tensor* y, float* stats, void* stream) {
+  PHS_REQUIRE(y && y->ptr && stats, "phs_chan_stats: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int HW = y->H * y->W;
+  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
+  int v = pick_vec(y);
+  dim3 grid; int ppb; size_t smem;
+  red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
+  PHS_REQUIRE(smem <= 48 * 1024, "phs_chan_stats: C=%d too large", y->C);
+  PHS_DISPATCH_DTYPE(y->dtype, T, PHS_DISPATCH_VEC(v, V, (chan_stats_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
+                                                            (const T*)y->ptr, HW, y->C, y->ld, ppb, stats))));
+  return phs_check_launch("chan_stats");
+}
+
+int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, int relu, float* sums, void* stream) {
+  PHS_REQUIRE(g && y && g->ptr && y->ptr && sums, "phs_norm_bwd_reduce: null argument");
+  PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C,
+              "phs_norm_bwd_reduce: g/y mismatch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int HW = y->H * y->W;
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
+  int v = min_vec(pick_vec(y), pick_vec(g));
+  dim3 grid; int ppb; size_t smem;
+  red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
+  PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce: C=%d too large", y->C);
+  PHS_DISPATCH_DTYPE(y->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (norm_bwd_reduce_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
+                                                (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
+                                                rstd, gamma, beta, relu, sums))));
+  return phs_check_launch("norm_bwd_reduce");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// finalize kernels (tiny): one thread per channel (BN) or per (n, channel) (GN)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int HW, int C, int mode, float eps,
+                                     float decay, float* moving_mean, float* moving_var, float* __restrict__ mean,
+                                     float* __restrict__ rstd) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == PHS_NORM_GN) {
+    if (idx >= N * C) return;
+    int n = idx / C, c = idx % C;
+    int G = max(2, C / 16);
+    int cpg = C / G;
+    int c0 = (c / cpg) * cpg;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      s += stats[((size_t)n * C + c0 + i) * 2];
+      q += stats[((size_t)n * C + c0 + i) * 2 + 1];
+    }
+    double cnt = (double)HW * cpg;
+    double m = s / cnt;
+    double var = q / cnt - m * m;
+    if (var < 0) var = 0;
+    mean[idx] = (float)m;
+    rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
+  } else {
+    if (idx >= C) return;
+    int c = idx;
+    float m, r;
+    if (mode == PHS_NORM_BN_TRAIN) {
+      double s = 0.0, q = 0.0;
+      for (int n = 0; n < N; ++n) {
+        s += stats[((size_t)n * C + c) * 2];
+        q += stats[((size_t)n * C + c) * 2 + 1];
+      }
+      double cnt = (double)HW * N;
+      double mm = s / cnt;
+      double var = q / cnt - mm * mm;
+      if (var < 0) var = 0;
+      m = (float)mm;
+      r = (float)(1.0 / sqrt(var + (double)eps));
+      if (moving_mean) {
+        double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * m;
+        moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)unb;
+      }
+    } else {
+      m = moving_mean[c];
+      r = rsqrtf(moving_var[c] + eps);
+    }
+    for (int n = 0; n < N; ++n) {
+      mean[(size_t)n * C + c] = m;
+      rstd[(size_t)n * C + c] = r;
+    }
+  }
+}
+
+int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
+                      float* moving_var, float* mean, float* rstd, void* stream) {
+  PHS_REQUIRE(mean && rstd, "phs_norm_finalize: null output");
+  PHS_REQUIRE(mode == PHS_NORM_BN_INFER || stats, "phs_norm_finalize: stats required");
+  PHS_REQUIRE(mode != PHS_NORM_BN_INFER || (moving_mean && moving_var), "phs_norm_finalize: moving stats required");
+  PHS_REQUIRE(mode != PHS_NORM_GN || C % max(2, C / 16) == 0, "phs_norm_finalize: C=%d not divisible into groups", C);
+  int total = mode == PHS_NORM_GN ? N * C : C;
+  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, N, HW, C, mode, eps, decay,
+                                                                            moving_mean, moving_var, mean, rstd);
+  return phs_check_launch("norm_finalize");
+}
+
+// backward finalize.  With g' = g*mask:  s1 = sum g', s2 = sum g'*xhat (per n,c).
+//   dbeta[c] = sum_n s1, dgamma[c] = sum_n s2
+//   BN: m1[c] = gamma*sum_n s1/(N*HW), m2[c] = gamma*sum_n s2/(N*HW)
+//   GN: m1[n,grp] = sum_{c in grp} gamma_c*s1/(cpg*HW), m2 likewise
+//   dx = rstd*(g'*gamma - m1 - xhat*m2);   dbias[c] = sum_{n,hw} dx  (closed form from the forward sums)
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd,
+                                         const float* __restrict__ gamma, int N, int HW, int C, int mode,
+                                         float* __restrict__ coef, float* dgamma, float* dbeta, float* dbias,
+                                         int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a1 = 0.0, a2 = 0.0, db = 0.0;
+  for (int n = 0; n < N; ++n) {
+    a1 += sums[((size_t)n * C + c) * 2];
+    a2 += sums[((size_t)n * C + c) * 2 + 1];
+  }
+  float ga = gamma[c];
+  if (mode == PHS_NORM_GN) {
+    int G = max(2, C / 16);
+    int cpg = C / G;
+    int c0 = (c / cpg) * cpg;
+    for (int n = 0; n < N; ++n) {
+      double m1 = 0.0, m2 = 0.0;
+      for (int i = 0; i < cpg; ++i) {
+        float gi = gamma[c0 + i];
+        m1 += (double)gi * sums[((size_t)n * C + c0 + i) * 2];
+        m2 += (double)gi * sums[((size_t)n * C + c0 + i) * 2 + 1];
+      }
+      double cnt = (double)HW * cpg;
+      m1 /= cnt;
+      m2 /= cnt;
+      coef[((size_t)n * C + c) * 2] = (float)m1;
+      coef[((size_t)n * C + c) * 2 + 1] = (float)m2;
+      if (dbias) {
+        double r = rstd[(size_t)n * C + c], mu = mean[(size_t)n * C + c];
+        double sx = (stats[((size_t)n * C + c) * 2] - (double)HW * mu) * r;  // sum_hw xhat
+        db += r * ((double)ga * sums[((size_t)n * C + c) * 2] - (double)HW * m1 - m2 * sx);
+      }
+    }
+  } else {
+    double cnt = (double)HW * N;
+    double m1 = ga * a1 / cnt, m2 = ga * a2 / cnt;
+    for (int n = 0; n < N; ++n) {
+      coef[((size_t)n * C + c) * 2] = (float)m1;
+      coef[((size_t)n * C + c) * 2 + 1] = (float)m2;
+    }
+    db = 0.0;  // batch norm removes any per-channel offset: the bias gradient is exactly zero
+  }
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)a2;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)a1;
+  if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)db;
+}
+
+int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* mean, const float* rstd,
+                          const float* gamma, int N, int HW, int C, int mode, float* coef, float* dgamma, float* dbeta,
+                          float* dbias, int accumulate, void* stream) {
+  PHS_REQUIRE(sums && mean && rstd && gamma && coef, "phs_norm_bwd_finalize: null argument");
+  PHS_REQUIRE(!dbias || stats, "phs_norm_bwd_finalize: dbias needs the forward stats");
+  PHS_REQUIRE(mode == PHS_NORM_GN || mode == PHS_NORM_BN_TRAIN, "phs_norm_bwd_finalize: mode %d has no backward", mode);
+  norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sums, stats, mean, rstd, gamma, N, HW, C, mode,
+                                                                         coef, dgamma, dbeta, dbias, accumulate);
+  return phs_check_launch("norm_bwd_finalize");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// streaming kernels: one thread per (pixel, channel-vector)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    norm_act_fwd_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C, int64_t total,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  const int nvec = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int n = (int)(pix / HW);
+    float v[V], o[V];
+    ldv<T, V>(y + pix * ldy + cv * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      int c = cv * V + k;
+      float sc = gamma[c] * rstd[(size_t)n * C + c];
+      float r = (v[k] - mean[(size_t)n * C + c]) * sc + beta[c];
+      o[k] = (relu && r < 0.f) ? 0.f : r;
+    }
+    stv<T, V>(a + pix * lda + cv * V, o);
+  }
+}
+
+int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     int relu, const phs_tensor* a, void* stream) {
+  PHS_REQUIRE(y && a && y->ptr && a->ptr && mean && rstd && gamma && beta, "phs_norm_act_fwd: null argument");
+  PHS_REQUIRE(y->dtype == a->dtype && y->N == a->N && y->H == a->H && y->W == a->W && y->C == a->C,
+              "phs_norm_act_fwd: y/a mismatch");
+  int v = min_vec(pick_vec(y), pick_vec(a));
+  int HW = y->H * y->W;
+  int64_t total = (int64_t)y->N * HW * (y->C / v);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (blocks < 1) blocks = 1;
+  PHS_DISPATCH_DTYPE(y->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_kernel<T, V><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, total, mean, rstd,
+                                                gamma, beta, relu))));
+  return phs_check_launch("norm_act_fwd");
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    norm_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dy,
+                          int lddy, int HW, int C, int64_t total, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, int relu, const float* __restrict__ coef) {
+  const int nvec = C / V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int n = (int)(pix / HW);
+    float gv[V], yv[V], o[V];
+    ldv<T, V>(g + pix * ldg + cv * V, gv);
+    ldv<T, V>(y + pix * ldy + cv * V, yv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      int c = cv * V + k;
+      size_t nc = (size_t)n * C + c;
+      float rs = rstd[nc];
+      float xh = (yv[k] - mean[nc]) * rs;
+      float aa = gamma[c] * xh + beta[c];
+      float gm = (relu && aa <= 0.f) ? 0.f : gv[k];
+      o[k] = rs * (gm * gamma[c] - coef[nc * 2] - xh * coef[nc * 2 + 1]);
+    }
+    stv<T, V>(dy + pix * lddy + cv * V, o);
+  }
+}
+
+int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, const float* coef, const phs_tensor* dy,
+                       void* stream) {
+  PHS_REQUIRE(g && y && dy && g->ptr && y->ptr && dy->ptr && coef, "phs_norm_bwd_apply: null argument");
+  PHS_REQUIRE(g->dtype == y->dtype && dy->dtype == y->dtype && g->C == y->C && dy->C == y->C && g->N == y->N &&
+                  g->H == y->H && g->W == y->W,
+              "phs_norm_bwd_apply: tensor mismatch");
+  int v = min_vec(min_vec(pick_vec(y), pick_vec(g)), pick_vec(dy));
+  int HW = y->H * y->W;
+  int64_t total = (int64_t)y->N * HW * (y->C / v);
+  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  if (blocks < 1) blocks = 1;
+  PHS_DISPATCH_DTYPE(y->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (norm_bwd_apply_kernel<T, V><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
+                                                HW, y->C, total, mean, rstd, gamma, beta, relu, coef))));
+  return phs_check_launch("norm_bwd_apply");
+}
+
+// ---- 2x2 average pool ------------------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    avgpool2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Ho, int Wo, int C,
+                        int64_t total) {
+  const int nvec = C / V;
+  const int Wi = Wo * 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int wo = (int)(pix % Wo);
+    int64_t t = pix / Wo;
+    int ho = (int)(t % Ho);
+    int64_t n = t / Ho;
+    const T* p = x + ((n * (2 * Ho) + 2 * ho) * Wi + 2 * wo) * (int64_t)ldx + cv * V;
+    float a[V], b[V], c[V], d[V], o[V];
+    ldv<T, V>(p, a);
+    ldv<T, V>(p + ldx, b);
+    ldv<T, V>(p + (int64_t)Wi * ldx, c);
+    ldv<T, V>(p + (int64_t)Wi * ldx + ldx, d);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = 0.25f * ((a[k] + b[k]) + (c[k] + d[k]));
+    stv<T, V>(y + pix * ldy + cv * V, o);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    avgpool2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, int C,
+                        int64_t total, int accumulate) {
+  const int nvec = C / V;
+  const int Wo = Wi / 2, Ho = Hi / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int w = (int)(pix % Wi);
+    int64_t t = pix / Wi;
+    int h = (int)(t % Hi);
+    int64_t n = t / Hi;
+    float g[V], o[V];
+    ldv<T, V>(dy + ((n * Ho + h / 2) * Wo + w / 2) * (int64_t)lddy + cv * V, g);
+    T* q = dx + pix * lddx + cv * V;
+    if (accumulate) {
+      ldv<T, V>(q, o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] += 0.25f * g[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] = 0.25f * g[k];
+    }
+    stv<T, V>(q, o);
+  }
+}
+
+static int stream_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int phs_avgpool2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
+  PHS_REQUIRE(x && y && x->ptr && y->ptr, "phs_avgpool2_fwd: null argument");
+  PHS_REQUIRE(x->dtype == y->dtype && x->N == y->N && x->C == y->C && x->H == 2 * y->H && x->W == 2 * y->W,
+              "phs_avgpool2_fwd: shape mismatch (%d,%d,%d)->(%d,%d,%d)", x->H, x->W, x->C, y->H, y->W, y->C);
+  int v = min_vec(pick_vec(x), pick_vec(y));
+  int64_t total = (int64_t)y->N * y->H * y->W * (y->C / v);
+  PHS_DISPATCH_DTYPE(x->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (avgpool2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, y->H, y->W, y->C, total))));
+  return phs_check_launch("avgpool2_fwd");
+}
+
+int phs_avgpool2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate, void* stream) {
+  PHS_REQUIRE(dx && dy && dx->ptr && dy->ptr, "phs_avgpool2_bwd: null argument");
+  PHS_REQUIRE(dx->dtype == dy->dtype && dx->N == dy->N && dx->C == dy->C && dx->H == 2 * dy->H && dx->W == 2 * dy->W,
+              "phs_avgpool2_bwd: shape mismatch");
+  int v = min_vec(pick_vec(dx), pick_vec(dy));
+  int64_t total = (int64_t)dx->N * dx->H * dx->W * (dx->C / v);
+  PHS_DISPATCH_DTYPE(dx->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (avgpool2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, dx->C, total,
+                                                accumulate))));
+  return phs_check_launch("avgpool2_bwd");
+}
+
+// ---- TF1 legacy bilinear x2 ------------------------------------------------------------------------------
+// forward: out[2k] = in[k]; out[2k+1] = 0.5*(in[k] + in[min(k+1,n-1)]) per axis
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Hi, int Wi, int C,
+                         int64_t total) {
+  const int nvec = C / V;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int wo = (int)(pix % Wo);
+    int64_t t = pix / Wo;
+    int ho = (int)(t % Ho);
+    int64_t n = t / Ho;
+    int h0 = ho >> 1, w0 = wo >> 1;
+    int h1 = (ho & 1) ? min(h0 + 1, Hi - 1) : h0;
+    int w1 = (wo & 1) ? min(w0 + 1, Wi - 1) : w0;
+    const T* b = x + n * Hi * Wi * (int64_t)ldx + cv * V;
+    float a[V], bb[V], c[V], d[V], o[V];
+    ldv<T, V>(b + ((int64_t)h0 * Wi + w0) * ldx, a);
+    ldv<T, V>(b + ((int64_t)h0 * Wi + w1) * ldx, bb);
+    ldv<T, V>(b + ((int64_t)h1 * Wi + w0) * ldx, c);
+    ldv<T, V>(b + ((int64_t)h1 * Wi + w1) * ldx, d);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float top = 0.5f * (a[k] + bb[k]);  // exact when w1 == w0
+      float bot = 0.5f * (c[k] + d[k]);
+      o[k] = 0.5f * (top + bot);
+    }
+    stv<T, V>(y + pix * ldy + cv * V, o);
+  }
+}
+
+// adjoint, gather form: per axis in[k] receives out[2k] (w 1), out[2k+1] (w .5, or 1 when k == n-1), out[2k-1] (w .5, k>=1)
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    upsample2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, int C,
+                         int64_t total, int accumulate) {
+  const int nvec = C / V;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(i % nvec);
+    int64_t pix = i / nvec;
+    int w = (int)(pix % Wi);
+    int64_t t = pix / Wi;
+    int h = (int)(t % Hi);
+    int64_t n = t / Hi;
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const T* b = dy + n * Ho * Wo * (int64_t)lddy + cv * V;
+#pragma unroll
+    for (int dh = -1; dh <= 1; ++dh) {
+      int ho = 2 * h + dh;
+      if (ho < 0) continue;
+      float wh = dh == 0 ? 1.f : (dh == 1 && h == Hi - 1 ? 1.f : 0.5f);
+#pragma unroll
+      for (int dw = -1; dw <= 1; ++dw) {
+        int wo = 2 * w + dw;
+        if (wo < 0) continue;
+        float ww = dw == 0 ? 1.f : (dw == 1 && w == Wi - 1 ? 1.f : 0.5f);
+        float g[V];
+        ldv<T, V>(b + ((int64_t)ho * Wo + wo) * lddy, g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += wh * ww * g[k];
+      }
+    }
+    T* q = dx + pix * lddx + cv * V;
+    if (accumulate) {
+      float o[V];
+      ldv<T, V>(q, o);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += o[k];
+    }
+    stv<T, V>(q, acc);
+  }
+}
+
+int phs_upsample2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
+  PHS_REQUIRE(x && y && x->ptr && y->ptr, "phs_upsample2_fwd: null argument");
+  PHS_REQUIRE(x->dtype == y->dtype && x->N == y->N && x->C == y->C && y->H == 2 * x->H && y->W == 2 * x->W,
+              "phs_upsample2_fwd: shape mismatch");
+  int v = min_vec(pick_vec(x), pick_vec(y));
+  int64_t total = (int64_t)y->N * y->H * y->W * (y->C / v);
+  PHS_DISPATCH_DTYPE(x->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (upsample2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, x->H, x->W, x->C, total))));
+  return phs_check_launch("upsample2_fwd");
+}
+
+int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate, void* stream) {
+  PHS_REQUIRE(dx && dy && dx->ptr && dy->ptr, "phs_upsample2_bwd: null argument");
+  PHS_REQUIRE(dx->dtype == dy->dtype && dx->N == dy->N && dx->C == dy->C && dy->H == 2 * dx->H && dy->W == 2 * dx->W,
+              "phs_upsample2_bwd: shape mismatch");
+  int v = min_vec(pick_vec(dx), pick_vec(dy));
+  int64_t total = (int64_t)dx->N * dx->H * dx->W * (dx->C / v);
+  PHS_DISPATCH_DTYPE(dx->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (upsample2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, dx->C, total,
+                                                accumulate))));
+  return phs_check_launch("upsample2_bwd");
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void copy_cast_kernel(const TS* __restrict__ s, int lds, TD* __restrict__ d, int ldd, int C, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t pix = i / C;
+    stf<TD>(d + pix * ldd + c, ldf<TS>(s + pix * lds + c));
+  }
+}
+
+int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream) {
+  PHS_REQUIRE(src && dst && src->ptr && dst->ptr, "phs_copy_cast: null argument");
+  PHS_REQUIRE(src->N == dst->N && src->H == dst->H && src->W == dst->W && src->C == dst->C, "phs_copy_cast: shape mismatch");
+  int64_t total = (int64_t)src->N * src->H * src->W * src->C;
+  cudaStream_t st = (cudaStream_t)stream;
+  int b = stream_blocks(total);
+  if (src->dtype == PHS_F32 && dst->dtype == PHS_F32)
+    copy_cast_kernel<float, float><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total);
+  else if (src->dtype == PHS_F32)
+    copy_cast_kernel<float, bf16><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total);
+  else if (dst->dtype == PHS_F32)
+    copy_cast_kernel<bf16, float><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total);
+  else
+    copy_cast_kernel<bf16, bf16><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total);
+  return phs_check_launch("copy_cast");
+}
+
+template <typename T>
+__global__ void posterior_input_kernel(const float* __restrict__ x, const uint8_t* __restrict__ s, int Cx, int nl,
+                                       T* __restrict__ out, int ld, int64_t npix) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    T* o = out + p * ld;
+    for (int c = 0; c < Cx; ++c) stf<T>(o + c, x[p * Cx + c]);
+    int lab = s[p];
+    for (int c = 0; c < nl; ++c) stf<T>(o + Cx + c, (c == lab ? 1.f : 0.f) - 0.5f);
+  }
+}
+
+int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, int Cx, int nlabels,
+                        const phs_tensor* out, void* stream) {
+  PHS_REQUIRE(x && s && out && out->ptr, "phs_posterior_input: null argument");
+  PHS_REQUIRE(out->C == Cx + nlabels && out->N == N && out->H == H && out->W == W, "phs_posterior_input: shape mismatch");
+  int64_t npix = (int64_t)N * H * W;
+  PHS_DISPATCH_DTYPE(out->dtype, T, (posterior_input_kernel<T><<<stream_blocks(npix), 256, 0, (cudaStream_t)stream>>>(
+                                        x, s, Cx, nlabels, (T*)out->ptr, out->ld, npix)));
+  return phs_check_launch("posterior_input");
+}
+
+template <typename T>
+__global__ void broadcast_z_kernel(const float* __restrict__ z, T* __restrict__ out, int ld, int HW, int zd, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % zd);
+    int64_t pix = i / zd;
+    int n = (int)(pix / HW);
+    stf<T>(out + pix * ld + c, z[n * zd + c]);
+  }
+}
+
+int phs_broadcast_z(const float* z, const phs_tensor* out, void* stream) {
+  PHS_REQUIRE(z && out && out->ptr, "phs_broadcast_z: null argument");
+  int HW = out->H * out->W;
+  int64_t total = (int64_t)out->N * HW * out->C;
+  PHS_DISPATCH_DTYPE(out->dtype, T, (broadcast_z_kernel<T><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                        z, (T*)out->ptr, out->ld, HW, out->C, total)));
+  return phs_check_launch("broadcast_z");
+}
+
+template <typename T>
+__global__ void broadcast_z_bwd_kernel(const T* __restrict__ g, int ld, int HW, int zd, float* __restrict__ dz, int accumulate) {
+  // one block per (n, c)
+  int n = blockIdx.x / zd, c = blockIdx.x % zd;
+  float a = 0.f;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) a += ldf<T>(g + ((int64_t)n * HW + p) * ld + c);
+  __shared__ float sm[256];
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dz[blockIdx.x] = (accumulate ? dz[blockIdx.x] : 0.f) + sm[0];
+}
+
+int phs_broadcast_z_bwd(const phs_tensor* g, float* dz, int accumulate, void* stream) {
+  PHS_REQUIRE(g && g->ptr && dz, "phs_broadcast_z_bwd: null argument");
+  int HW = g->H * g->W;
+  PHS_DISPATCH_DTYPE(g->dtype, T, (broadcast_z_bwd_kernel<T><<<g->N * g->C, 256, 0, (cudaStream_t)stream>>>(
+                                      (const T*)g->ptr, g->ld, HW, g->C, dz, accumulate)));
+  return phs_check_launch("broadcast_z_bwd");
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+int phs_fill_f32(float* p, int64_t n, float v, void* stream) {
+  PHS_REQUIRE(p || n == 0, "phs_fill_f32: null");
+  if (n == 0) return 0;
+  fill_kernel<<<stream_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  return phs_check_launch("fill");
+}
+__global__ void axpy_kernel(float* d, const float* s, int64_t n, float alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] += alpha * s[i];
+}
+int phs_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream) {
+  PHS_REQUIRE((dst && src) || n == 0, "phs_axpy_f32: null");
+  if (n == 0) return 0;
+  axpy_kernel<<<stream_blocks(n), 256, 0, (cudaStream_t)stream>>>(dst, src, n, alpha);
+  return phs_check_launch("axpy");
+}
+
+// out[0] += scale * sum(src^2)  (tf.nn.l2_loss stack of add_weight_decay, phiseg_model.py:290-300)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ s, int64_t n, float scale, float* out) {
+  float a = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += s[i] * s[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    atomicAdd(out, t * scale);
+  }
+}
+int phs_sumsq_f32(const float* src, int64_t n, float scale, float* out, void* stream) {
+  PHS_REQUIRE((src && out) || n == 0, "phs_sumsq_f32: null");
+  if (n == 0) return 0;
+  int64_t b = (n + 255) / 256;
+  if (b > 296) b = 296;
+  sumsq_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(src, n, scale, out);
+  return phs_check_launch("sumsq");
+}
+
+// argmax over the last axis of [npix, nl] (np.argmax of the accumulated softmax in predict, phiseg_model.py:351-353):
+// first maximal index, like numpy.
+__global__ void argmax_kernel(const float* __restrict__ s, int64_t npix, int nl, int64_t* __restrict__ out) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    float mx = s[p * nl];
+    int am = 0;
+    for (int c = 1; c < nl; ++c) {
+      float v = s[p * nl + c];
+      if (v > mx) { mx = v; am = c; }
+    }
+    out[p] = am;
+  }
+}
+int phs_argmax_f32(const float* src, int64_t npix, int nlabels, int64_t* out, void* stream) {
+  PHS_REQUIRE((src && out) || npix == 0, "phs_argmax_f32: null");
+  PHS_REQUIRE(nlabels >= 1, "phs_argmax_f32: nlabels");
+  if (npix == 0) return 0;
+  argmax_kernel<<<stream_blocks(npix), 256, 0, (cudaStream_t)stream>>>(src, npix, nlabels, out);
+  return phs_check_launch("argmax");
+}

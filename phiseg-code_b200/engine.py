@@ -1,0 +1,775 @@
+"""Host-side engine of the B200-native PHiSeg path.
+
+It turns an architecture description (the graph phiseg/phiseg_model.py:37-141 builds out of
+phiseg/model_zoo/{posteriors,priors,likelihoods}.py) into *static programs*: flat lists of C-ABI kernel launches
+with pre-bound arguments over statically allocated NHWC device buffers.  A program is built once per
+(kind, batch size), replayed every step, and can be captured into a CUDA graph because nothing in it allocates,
+synchronises or depends on host values (the Adam step size is read from device memory).
+
+Backward is hand-written: every forward op pushes an emitter on a tape, the tape is walked in reverse to lay down
+the adjoint launches (SURVEY.md section 8a "backward obligations").  PyTorch is used for device memory, streams,
+the RNG for eps and torch.distributed; every arithmetic step of the path is a kernel of libphiseg_sm100.so.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+BN_EPS, BN_DECAY, GN_EPS = 1e-3, 0.99, 1e-5   # tfwrapper/normalisation.py:145,157 and :17
+
+
+def num_channels(n0):
+    """posteriors.py:59, priors.py:54, likelihoods.py:168"""
+    return [n0, 2 * n0, 4 * n0, 6 * n0, 6 * n0, 6 * n0, 6 * n0]
+
+
+class NetConfig:
+    """Plain description of the network + loss + optimizer, derived from an experiment module by phiseg_model."""
+
+    def __init__(self, arch='phiseg', image_size=(128, 128, 1), nlabels=2, zdim0=2, n0=32, resolution_levels=7,
+                 latent_levels=5, norm='batch_norm', KL_weight=1.0, xent_weight=1.0, exponential_weighting=True,
+                 weight_decay=None, optimizer='adam', mode='parity'):
+        assert arch in ('phiseg', 'probunet'), arch
+        assert norm in ('batch_norm', 'group_norm'), norm
+        assert mode in ('parity', 'fast'), mode
+        self.arch = arch
+        self.H, self.W, self.Cx = image_size
+        self.nlabels, self.zdim0, self.n0 = nlabels, zdim0, n0
+        self.R, self.L = resolution_levels, latent_levels
+        self.norm = norm
+        self.KL_weight, self.xent_weight = KL_weight, xent_weight
+        self.exponential_weighting = exponential_weighting
+        self.weight_decay = weight_decay
+        self.optimizer = optimizer
+        self.mode = mode
+        self.nc = num_channels(n0)
+        if arch == 'probunet':
+            assert latent_levels == 1
+        d = 1 << (resolution_levels - 1)
+        if self.H % d or self.W % d:
+            raise ValueError('image size %dx%d is not divisible by 2^(resolution_levels-1)=%d' % (self.H, self.W, d))
+
+    def latent_shapes(self, B):
+        if self.arch == 'probunet':
+            return [(B, self.zdim0)]
+        d = self.R - self.L
+        return [(B, self.H >> (i + d), self.W >> (i + d), self.zdim0) for i in range(self.L)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameters
+# ------------------------------------------------------------------------------------------------------------
+def build_spec(cfg):
+    """Variables in TF graph-construction order with the names the reference's variable scopes produce
+    (layers.py:119-131, normalisation.py:24-25,156, phiseg_model.py:37-98).  Returns [(name, shape, kind)],
+    kind in W, b, gamma, beta, moving_mean, moving_variance.  Includes the dead z*_ups_to_* branches of
+    posteriors.py:112-118 (they own variables but feed nothing; they never receive a gradient)."""
+    ent = []
+    nc, R, Lv, z0, n0, nrm = cfg.nc, cfg.R, cfg.L, cfg.zdim0, cfg.n0, cfg.norm
+
+    def conv(scope, k, cin, cout, normed, bias=None):
+        ent.append((scope + '/W', (k, k, cin, cout), 'W'))
+        has_bias = not (normed and nrm == 'batch_norm') if bias is None else bias
+        if has_bias:
+            ent.append((scope + '/b', (cout,), 'b'))
+        if normed:
+            if nrm == 'batch_norm':
+                pre = scope + '/batch_norm/BatchNorm/'
+                ent.extend([(pre + 'beta', (cout,), 'beta'), (pre + 'gamma', (cout,), 'gamma'),
+                            (pre + 'moving_mean', (cout,), 'moving_mean'),
+                            (pre + 'moving_variance', (cout,), 'moving_variance')])
+            else:
+                ent.extend([(scope + '/group_norm/gamma', (1, 1, 1, cout), 'gamma'),
+                            (scope + '/group_norm/beta', (1, 1, 1, cout), 'beta')])
+
+    if cfg.arch == 'phiseg':
+        d = R - Lv
+        for net, cin0 in (('posterior', cfg.Cx + cfg.nlabels), ('prior', cfg.Cx)):
+            for i in range(R):
+                conv('%s/z%d_pre_1' % (net, i), 3, cin0 if i == 0 else nc[i - 1], nc[i], True)
+                conv('%s/z%d_pre_2' % (net, i), 3, nc[i], nc[i], True)
+                conv('%s/z%d_pre_3' % (net, i), 3, nc[i], nc[i], True)
+            for i in reversed(range(Lv)):
+                if i == Lv - 1:
+                    conv('%s/z%d_mu' % (net, i), 3, nc[i + d], z0, False)
+                    conv('%s/z%d_sigma' % (net, i), 1, nc[i + d], z0, False)
+                else:
+                    for j in reversed(range(i + 1)):
+                        conv('%s/z%d_ups_to_%d_c_1' % (net, i + 1, j + 1), 3, z0 if j == i else z0 * n0, z0 * n0, True)
+                        conv('%s/z%d_ups_to_%d_c_2' % (net, i + 1, j + 1), 3, z0 * n0, z0 * n0, True)
+                    conv('%s/z%d_input_1' % (net, i), 3, nc[i + d] + z0 * n0, nc[i], True)
+                    conv('%s/z%d_input_2' % (net, i), 3, nc[i], nc[i], True)
+                    conv('%s/z%d_mu' % (net, i), 1, nc[i], z0, False)
+                    conv('%s/z%d_sigma' % (net, i), 1, nc[i], z0, False)
+        net = 'likelihood'
+        for i in range(Lv):
+            conv('%s/z%d_post_1' % (net, i), 3, z0, nc[i], True)
+            conv('%s/z%d_post_2' % (net, i), 3, nc[i], nc[i], True)
+            for t in range(d):
+                conv('%s/preups_%d/z%d_post' % (net, i, t), 3, nc[i], nc[i], True)
+        for i in reversed(range(Lv - 1)):
+            below = nc[Lv - 1] if i + 1 == Lv - 1 else nc[i + 1 + d]
+            conv('%s/post_z%d_ups_c' % (net, i + 1), 3, below, nc[i], True)
+            conv('%s/post_c_%d_1' % (net, i), 3, 2 * nc[i], nc[i + d], True)
+            conv('%s/post_c_%d_2' % (net, i), 3, nc[i + d], nc[i + d], True)
+        for i in range(Lv):
+            conv('%s/y_lvl%d' % (net, i), 1, nc[Lv - 1] if i == Lv - 1 else nc[i + d], cfg.nlabels, False)
+    else:
+        # prob_unet2D passes add_bias explicitly (posteriors.py:25): off under batch_norm, on otherwise
+        for net, cin0 in (('posterior', cfg.Cx + cfg.nlabels), ('prior', cfg.Cx)):
+            for i in range(R):
+                for t in (1, 2, 3):
+                    conv('%s/conv_%d_%d' % (net, i, t), 3, (cin0 if i == 0 else nc[i - 1]) if t == 1 else nc[i], nc[i], True)
+            conv('%s/pre_mu' % net, 1, nc[R - 1], z0, False)
+            conv('%s/pre_sigma' % net, 1, nc[R - 1], z0, False)
+        net = 'likelihood'
+        for i in range(R):
+            for t in (1, 2, 3):
+                conv('%s/encoder/conv_%d_%d' % (net, i, t), 3, (cfg.Cx if i == 0 else nc[i - 1]) if t == 1 else nc[i], nc[i], True)
+        prev = nc[R - 1]
+        for jj in range(R - 1):
+            ii = R - jj - 1
+            conv('%s/decoder/conv_%d_1' % (net, jj), 3, prev + nc[ii - 1], nc[ii], True)
+            conv('%s/decoder/conv_%d_2' % (net, jj), 3, nc[ii], nc[ii], True)
+            conv('%s/decoder/conv_%d_3' % (net, jj), 3, nc[ii], nc[ii], True)
+            prev = nc[ii]
+        conv('%s/recomb_0' % net, 1, prev + z0, nc[0], True)
+        conv('%s/recomb_1' % net, 1, nc[0], nc[0], True)
+        conv('%s/recomb_2' % net, 1, nc[0], nc[0], True)
+        conv('%s/prediction' % net, 1, nc[0], cfg.nlabels, False)
+    return ent
+
+
+def he_normal(gen, shape):
+    """tfwrapper/utils.py:225-226: variance_scaling_initializer(factor=2, mode=FAN_IN, uniform=False), i.e. a
+    normal truncated at +-2 sigma (resampled) with sigma = sqrt(1.3 * 2 / fan_in), fan_in = kh*kw*Cin."""
+    fan_in = shape[0] * shape[1] * shape[2]
+    std = math.sqrt(1.3 * 2.0 / fan_in)
+    w = torch.randn(shape, generator=gen, dtype=torch.float32)
+    bad = w.abs() > 2.0
+    while bool(bad.any()):
+        w[bad] = torch.randn(int(bad.sum()), generator=gen, dtype=torch.float32)
+        bad = w.abs() > 2.0
+    return w * std
+
+
+def tc_eligible(k, cin, cout):
+    """Shapes the tcgen05 implicit-GEMM kernels take (conv_tc.cu)."""
+    return cin % 32 == 0 and cout % 16 == 0 and 16 <= cout <= 256
+
+
+class Params:
+    """Flat fp32 master / gradient / optimizer-slot buffers addressed through a name table, plus the BN moving
+    statistics and (fast mode) the bf16 filter shadows the tensor-core kernels read."""
+
+    def __init__(self, cfg, device):
+        self.cfg, self.device = cfg, device
+        self.spec = build_spec(cfg)
+        self.table, self.state_table = {}, {}
+        off = soff = 0
+        for name, shape, kind in self.spec:
+            n = int(np.prod(shape))
+            if kind in ('moving_mean', 'moving_variance'):
+                self.state_table[name] = (soff, shape, kind)
+                soff += n
+            else:
+                self.table[name] = (off, shape, kind)
+                off += (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        self.n = off
+        self.p = torch.zeros(off, dtype=torch.float32, device=device)
+        self.g = torch.zeros(off, dtype=torch.float32, device=device)
+        self.slots = None                        # (m, v) or (acc,) created at the first optimizer step
+        self.state = torch.zeros(max(soff, 1), dtype=torch.float32, device=device)
+        self.step = 0
+        # tensor-core shadows
+        self.shadow = None
+        self.shadow_table = {}
+        self.prep_table = None
+        if cfg.mode == 'fast':
+            rows, soff = [], 0
+            for name, shape, kind in self.spec:
+                if kind == 'W' and tc_eligible(shape[0], shape[2], shape[3]):
+                    n = int(np.prod(shape))
+                    taps = shape[0] * shape[1]
+                    self.shadow_table[name] = (soff, soff + n)
+                    rows.append([self.table[name][0], soff, soff + n, taps, shape[2], shape[3]])
+                    soff += 2 * n
+            self.shadow = torch.zeros(max(soff, 8), dtype=torch.bfloat16, device=device)
+            self.prep_table = torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1, 6)
+        self.init()
+
+    # -- views ------------------------------------------------------------------------------------------
+    def view(self, name, buf=None):
+        if name in self.table:
+            off, shape, _ = self.table[name]
+            return (self.p if buf is None else buf)[off:off + int(np.prod(shape))].view(shape)
+        off, shape, _ = self.state_table[name]
+        return self.state[off:off + int(np.prod(shape))].view(shape)
+
+    def ptr(self, name, which='p'):
+        if name in self.table:
+            base = {'p': self.p, 'g': self.g}[which]
+            return base.data_ptr() + 4 * self.table[name][0]
+        return self.state.data_ptr() + 4 * self.state_table[name][0]
+
+    def has(self, name):
+        return name in self.table or name in self.state_table
+
+    def shadow_ptr(self, name, dgrad):
+        off = self.shadow_table[name][1 if dgrad else 0]
+        return self.shadow.data_ptr() + 2 * off
+
+    def names(self):
+        return [n for n, _, _ in self.spec]
+
+    # -- init / io --------------------------------------------------------------------------------------
+    def init(self, seed=1234):
+        """he_normal filters, zero biases, gamma=1, beta=0, moving_mean=0, moving_variance=1
+        (tfwrapper/utils.py:214-271; tf.contrib.layers.batch_norm defaults)."""
+        gen = torch.Generator().manual_seed(seed)
+        for name, shape, kind in self.spec:
+            if kind == 'W':
+                v = he_normal(gen, shape)
+            elif kind in ('gamma', 'moving_variance'):
+                v = torch.ones(shape)
+            else:
+                v = torch.zeros(shape)
+            self.view(name).copy_(v.to(self.device))
+        self.slots = None
+        self.step = 0
+        self.refresh_shadow()
+
+    def refresh_shadow(self, stream=None):
+        if self.shadow is None or self.prep_table.numel() == 0 or self.p.device.type != 'cuda':
+            return
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        L.check(L.load().phs_weight_prep(self.p.data_ptr(), self.shadow.data_ptr(), self.prep_table.data_ptr(),
+                                         self.prep_table.shape[0], st), 'phs_weight_prep')
+
+    def state_dict(self):
+        return {n: self.view(n).detach().cpu().clone() for n in self.names()}
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [n for n in self.names() if n not in sd]
+        if strict and missing:
+            raise KeyError('missing variables: %s' % missing[:5])
+        for n in self.names():
+            if n in sd:
+                v = torch.as_tensor(np.asarray(sd[n]) if not torch.is_tensor(sd[n]) else sd[n])
+                self.view(n).copy_(v.to(torch.float32).reshape(self.view(n).shape).to(self.device))
+        self.refresh_shadow()
+
+    def ensure_slots(self):
+        if self.slots is None:
+            k = 2 if self.cfg.optimizer == 'adam' else 1
+            self.slots = tuple(torch.zeros_like(self.p) for _ in range(k))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# device buffers
+# ------------------------------------------------------------------------------------------------------------
+_TORCH_DT = {L.PHS_F32: torch.float32, L.PHS_BF16: torch.bfloat16}
+_ES = {L.PHS_F32: 4, L.PHS_BF16: 2}
+
+
+class Buf:
+    """One NHWC allocation [N,H,W,ld]; its gradient twin is created on demand."""
+
+    def __init__(self, prog, N, H, W, ld, dtype, zero=False):
+        self.prog, self.N, self.H, self.W, self.ld, self.dtype = prog, N, H, W, ld, dtype
+        f = torch.zeros if zero else torch.empty
+        self.t = f((N, H, W, ld), dtype=_TORCH_DT[dtype], device=prog.device)
+        prog.bytes += self.t.numel() * _ES[dtype]
+        self.gbuf = None
+        self.gw = []          # channel ranges of the gradient already written by an adjoint launch
+
+    def act(self, c_off=0, C=None):
+        return Act(self, c_off, self.ld - c_off if C is None else C)
+
+
+class Act:
+    """A channel slice [c_off, c_off+C) of a Buf: the unit every kernel addresses (pitch = buf.ld)."""
+
+    def __init__(self, buf, c_off, C):
+        self.buf, self.c_off, self.C = buf, c_off, C
+        self._desc = None
+
+    N = property(lambda s: s.buf.N)
+    H = property(lambda s: s.buf.H)
+    W = property(lambda s: s.buf.W)
+    dtype = property(lambda s: s.buf.dtype)
+
+    @property
+    def ptr(self):
+        return self.buf.t.data_ptr() + self.c_off * _ES[self.buf.dtype]
+
+    def desc(self):
+        if self._desc is None:
+            self._desc = L.phs_tensor(self.ptr, self.N, self.H, self.W, self.C, self.buf.ld, self.buf.dtype)
+        return ctypes.byref(self._desc)
+
+    def tensor(self):
+        return self.buf.t[..., self.c_off:self.c_off + self.C]
+
+    # gradient bookkeeping (static, at program-build time)
+    def grad(self):
+        b = self.buf
+        if b.gbuf is None:
+            b.gbuf = Buf(b.prog, b.N, b.H, b.W, b.ld, b.dtype)
+        return Act(b.gbuf, self.c_off, self.C)
+
+    def grad_written(self):
+        lo, hi = self.c_off, self.c_off + self.C
+        for a, b in self.buf.gw:
+            if a <= lo and hi <= b:
+                return True
+            if not (hi <= a or b <= lo):
+                raise AssertionError('partially written gradient range (%d,%d) vs (%d,%d)' % (lo, hi, a, b))
+        return False
+
+    def mark_grad_written(self):
+        lo, hi = self.c_off, self.c_off + self.C
+        self.buf.gw = [(a, b) for a, b in self.buf.gw if not (lo <= a and b <= hi)] + [(lo, hi)]
+
+
+class Program:
+    """A replayable list of kernel launches."""
+
+    def __init__(self, device):
+        self.device = device
+        self.steps = []
+        self.keep = []
+        self.bytes = 0
+        self.lib = L.load()
+        self.graph = None
+
+    def emit(self, name, *args):
+        self.steps.append((getattr(self.lib, name), args, name))
+
+    def vec(self, n, zero=False):
+        t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        self.bytes += 4 * t.numel()
+        return t
+
+    def run_eager(self, steps=None):
+        st = torch.cuda.current_stream().cuda_stream
+        for fn, args, name in (self.steps if steps is None else steps):
+            rc = fn(*args, st)
+            if rc:
+                L.check(rc, name)
+
+    def launches(self):
+        return len(self.steps)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# graph builder
+# ------------------------------------------------------------------------------------------------------------
+class Builder:
+    """Lays down forward launches immediately and records adjoint emitters on a tape."""
+
+    def __init__(self, cfg, params, B, training, want_grad, device):
+        self.cfg, self.P, self.B = cfg, params, B
+        self.training, self.want_grad = training, want_grad
+        self.prog = Program(device)
+        self.fwd_steps = self.prog.steps
+        self.tape = []
+        self.adt = L.PHS_BF16 if cfg.mode == 'fast' else L.PHS_F32      # activation dtype
+        self.n_conv_flop = 0
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
+        return Buf(self.prog, N, H, W, C if ld is None else ld, self.adt if dtype is None else dtype, zero).act(0, C)
+
+    def emit(self, name, *args):
+        self.prog.emit(name, *args)
+
+    def _norm_mode(self):
+        if self.cfg.norm == 'group_norm':
+            return L.NORM_GN, GN_EPS
+        return (L.NORM_BN_TRAIN if self.training else L.NORM_BN_INFER), BN_EPS
+
+    # -- layers.conv2D (tfwrapper/layers.py:94-145) ----------------------------------------------------------
+    def conv(self, x, scope, k, cout, normed=True, relu=True, out=None, need_dx=True, out_dtype=None):
+        P, cfg, pr = self.P, self.cfg, self.prog
+        wname = scope + '/W'
+        cin = x.C
+        assert P.table[wname][1] == (k, k, cin, cout), (scope, P.table[wname][1], (k, k, cin, cout))
+        bias = P.ptr(scope + '/b') if P.has(scope + '/b') else None
+        tc = (cfg.mode == 'fast' and tc_eligible(k, cin, cout) and x.dtype == L.PHS_BF16
+              and (out_dtype in (None, L.PHS_BF16)))
+        impl = L.IMPL_TC if tc else L.IMPL_SIMT
+        w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
+        w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
+        self.n_conv_flop += 2 * x.N * x.H * x.W * k * k * cin * cout
+        ydt = self.adt if out_dtype is None else out_dtype
+        if not normed:
+            y = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
+            self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
+            a = y
+            nb = None
+        else:
+            y = self.new(x.N, x.H, x.W, cout, ydt)
+            self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
+            mode, eps = self._norm_mode()
+            N, HW, C = x.N, x.H * x.W, cout
+            if cfg.norm == 'batch_norm':
+                pre = scope + '/batch_norm/BatchNorm/'
+                gamma, beta = P.ptr(pre + 'gamma'), P.ptr(pre + 'beta')
+                dgamma, dbeta = P.ptr(pre + 'gamma', 'g'), P.ptr(pre + 'beta', 'g')
+                mm, mv = P.ptr(pre + 'moving_mean'), P.ptr(pre + 'moving_variance')
+            else:
+                pre = scope + '/group_norm/'
+                gamma, beta = P.ptr(pre + 'gamma'), P.ptr(pre + 'beta')
+                dgamma, dbeta = P.ptr(pre + 'gamma', 'g'), P.ptr(pre + 'beta', 'g')
+                mm = mv = None
+            stats = pr.vec(N * C * 2)
+            mean, rstd = pr.vec(N * C), pr.vec(N * C)
+            if mode != L.NORM_BN_INFER:
+                self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
+            self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
+                      rstd.data_ptr())
+            a = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
+            self.emit('phs_norm_act_fwd', y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+            nb = (mode, stats, mean, rstd, gamma, beta, dgamma, dbeta)
+
+        if self.want_grad:
+            def bwd():
+                ga = a.grad()
+                assert a.grad_written(), 'no gradient reaches %s' % scope
+                if nb is not None:
+                    mode, stats, mean, rstd, gamma, beta, dgamma, dbeta = nb
+                    N, HW, C = x.N, x.H * x.W, cout
+                    sums, coef = pr.vec(N * C * 2), pr.vec(N * C * 2)
+                    dy = self.new(x.N, x.H, x.W, cout, y.dtype)
+                    dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
+                    self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
+                              int(relu), sums.data_ptr())
+                    self.emit('phs_norm_bwd_finalize', sums.data_ptr(), stats.data_ptr(), mean.data_ptr(),
+                              rstd.data_ptr(), gamma, N, HW, C, mode, coef.data_ptr(), dgamma, dbeta, dbias, 1)
+                    self.emit('phs_norm_bwd_apply', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
+                              int(relu), coef.data_ptr(), dy.desc())
+                    db = None
+                else:
+                    dy = ga
+                    db = P.ptr(scope + '/b', 'g') if bias is not None else None
+                self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
+                if need_dx:
+                    gx = x.grad()
+                    acc = int(x.grad_written())
+                    self.emit('phs_conv2d', dy.desc(), w_d, None, gx.desc(), k, 1, acc, impl)
+                    x.mark_grad_written()
+            self.tape.append(bwd)
+        return a
+
+    # -- layers.averagepool2D (tfwrapper/layers.py:44-54) ---------------------------------------------------
+    def pool(self, x, out=None):
+        y = out if out is not None else self.new(x.N, x.H // 2, x.W // 2, x.C, x.dtype)
+        self.emit('phs_avgpool2_fwd', x.desc(), y.desc())
+        if self.want_grad:
+            def bwd():
+                assert y.grad_written()
+                self.emit('phs_avgpool2_bwd', y.grad().desc(), x.grad().desc(), int(x.grad_written()))
+                x.mark_grad_written()
+            self.tape.append(bwd)
+        return y
+
+    # -- layers.bilinear_upsample2D (tfwrapper/layers.py:336-345) -------------------------------------------
+    def up(self, x, out=None, need_dx=True):
+        y = out if out is not None else self.new(x.N, x.H * 2, x.W * 2, x.C, x.dtype)
+        self.emit('phs_upsample2_fwd', x.desc(), y.desc())
+        if self.want_grad and need_dx:
+            def bwd():
+                assert y.grad_written()
+                self.emit('phs_upsample2_bwd', y.grad().desc(), x.grad().desc(), int(x.grad_written()))
+                x.mark_grad_written()
+            self.tape.append(bwd)
+        return y
+
+    def emit_backward(self):
+        for f in reversed(self.tape):
+            f()
+        self.tape = []
+
+
+# ------------------------------------------------------------------------------------------------------------
+# networks
+# ------------------------------------------------------------------------------------------------------------
+class StepProgram:
+    """One built graph: inputs, outputs and the launch lists (forward [+ backward])."""
+    pass
+
+
+def _ptr_array(ptrs):
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    return arr
+
+
+def build_program(cfg, params, B, kind, device):
+    """kind:
+      'train'      posterior + prior(generation_mode=False) + likelihood(posterior z) + ELBO, backward
+                   (phiseg_model.py:37-59,75-83,113-141), training=True
+      'eval'       the same forward with training=False (validation losses, phiseg_model.py:537-549)
+      'sample'     prior(generation_mode=True) + likelihood(prior z) + aggregate (phiseg_model.py:61-109), training=False
+      'posterior'  posterior only, training=False (generate_posterior_samples, :484-495)
+      'from_z'     likelihood on given z (generate_samples_from_z, :313-322), training=False
+    """
+    training = kind == 'train'
+    want_grad = kind == 'train'
+    b = Builder(cfg, params, B, training, want_grad, device)
+    pr = b.prog
+    sp = StepProgram()
+    sp.kind, sp.B, sp.prog, sp.cfg = kind, B, pr, cfg
+    H, W, Cx, nl, Lv, R, zd = cfg.H, cfg.W, cfg.Cx, cfg.nlabels, cfg.L, cfg.R, cfg.zdim0
+    nc = cfg.nc
+    f32 = L.PHS_F32
+    # --- inputs
+    sp.x = b.new(B, H, W, Cx, f32)
+    sp.s = torch.zeros((B, H, W), dtype=torch.uint8, device=device)
+    shapes = cfg.latent_shapes(B)
+    sp.eps = [torch.zeros(s, dtype=torch.float32, device=device) for s in shapes]
+    sp.losses = torch.zeros(2 * Lv + 2, dtype=torch.float32, device=device)   # [xent_l | KL_l | pad]
+    need_post = kind in ('train', 'eval', 'posterior')
+    need_prior = kind in ('train', 'eval', 'sample')
+    need_lik = kind in ('train', 'eval', 'sample', 'from_z')
+    gen_mode = kind == 'sample'
+
+    if kind in ('train', 'eval'):
+        pr.emit('phs_fill_f32', sp.losses.data_ptr(), sp.losses.numel(), 0.0)
+
+    nets = []
+    if need_post:
+        pin = b.new(B, H, W, Cx + nl)
+        pr.emit('phs_posterior_input', sp.x.ptr, sp.s.data_ptr(), B, H, W, Cx, nl, pin.desc())
+        nets.append(('posterior', pin))
+    if need_prior:
+        nets.append(('prior', sp.x))
+
+    sp.z = sp.mu = sp.sigma = sp.prior_mu = sp.prior_sigma = None
+    if cfg.arch == 'phiseg':
+        d = R - Lv
+        zbufs = {}
+        if nets:
+            # --- encoders (posteriors.py:84-95): pre_z[r]; levels that are concatenated later are written
+            # straight into the first channels of their concat buffer (tf.concat at posteriors.py:120 is free)
+            pre_z = {}
+            cat = {}
+            for net, inp in nets:
+                h = inp
+                for r in range(R):
+                    if r > 0:
+                        h = b.pool(h)
+                    h = b.conv(h, '%s/z%d_pre_1' % (net, r), 3, nc[r], need_dx=r > 0)
+                    h = b.conv(h, '%s/z%d_pre_2' % (net, r), 3, nc[r])
+                    out = None
+                    l = r - d
+                    if 0 <= l < Lv - 1:
+                        cbuf = Buf(pr, B, H >> r, W >> r, nc[r] + zd * cfg.n0, b.adt)
+                        cat[(net, l)] = cbuf
+                        out = cbuf.act(0, nc[r])
+                    h = b.conv(h, '%s/z%d_pre_3' % (net, r), 3, nc[r], out=out)
+                    pre_z[(net, r)] = h
+            # --- latent hierarchy, posterior and prior level by level (posteriors.py:98-130, priors.py:92-126)
+            mu = {n: [None] * Lv for n, _ in nets}
+            spre = {n: [None] * Lv for n, _ in nets}
+            sig = {n: [None] * Lv for n, _ in nets}
+            zl = [None] * Lv
+            for l in reversed(range(Lv)):
+                hl, wl = H >> (l + d), W >> (l + d)
+                for net, _ in nets:
+                    if l == Lv - 1:
+                        src = pre_z[(net, l + d)]
+                        mu[net][l] = b.conv(src, '%s/z%d_mu' % (net, l), 3, zd, normed=False, out_dtype=f32)
+                        spre[net][l] = b.conv(src, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
+                    else:
+                        u = b.up(zl[l + 1])
+                        u = b.conv(u, '%s/z%d_ups_to_%d_c_1' % (net, l + 1, l + 1), 3, zd * cfg.n0)
+                        cbuf = cat[(net, l)]
+                        b.conv(u, '%s/z%d_ups_to_%d_c_2' % (net, l + 1, l + 1), 3, zd * cfg.n0,
+                               out=cbuf.act(nc[l + d], zd * cfg.n0))
+                        zin = b.conv(cbuf.act(), '%s/z%d_input_1' % (net, l), 3, nc[l])
+                        zin = b.conv(zin, '%s/z%d_input_2' % (net, l), 3, nc[l])
+                        mu[net][l] = b.conv(zin, '%s/z%d_mu' % (net, l), 1, zd, normed=False, out_dtype=f32)
+                        spre[net][l] = b.conv(zin, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
+                    sig[net][l] = b.new(B, hl, wl, zd, f32)
+                zl[l] = b.new(B, hl, wl, zd, f32)
+                _emit_latent(b, sp, l, hl * wl, mu, spre, sig, zl[l], gen_mode, need_post, need_prior, gap=0)
+            sp.z = zl
+            if need_post:
+                sp.mu, sp.sigma = mu['posterior'], sig['posterior']
+            if need_prior:
+                sp.prior_mu, sp.prior_sigma = mu['prior'], sig['prior']
+        else:
+            sp.z = [b.new(*shapes[l], f32) for l in range(Lv)]          # fed by the caller ('from_z')
+        if need_lik:
+            sp.logits = _phiseg_likelihood(b, cfg, sp.z)
+    else:
+        if nets:
+            mu = {n: [None] for n, _ in nets}
+            spre = {n: [None] for n, _ in nets}
+            sig = {n: [None] for n, _ in nets}
+            mu_out = {n: [None] for n, _ in nets}
+            for net, inp in nets:
+                h = inp
+                for r in range(R):
+                    if r > 0:
+                        h = b.pool(h)
+                    for t in (1, 2, 3):
+                        h = b.conv(h, '%s/conv_%d_%d' % (net, r, t), 3, nc[r], need_dx=not (r == 0 and t == 1))
+                mu[net][0] = b.conv(h, '%s/pre_mu' % net, 1, zd, normed=False, out_dtype=f32)
+                spre[net][0] = b.conv(h, '%s/pre_sigma' % net, 1, zd, normed=False, out_dtype=f32)
+                sig[net][0] = b.new(B, 1, 1, zd, f32)
+                mu_out[net][0] = b.new(B, 1, 1, zd, f32)
+            z = b.new(B, 1, 1, zd, f32)
+            hw = (H >> (R - 1)) * (W >> (R - 1))
+            _emit_latent(b, sp, 0, hw, mu, spre, sig, z, gen_mode, need_post, need_prior, gap=1, mu_out=mu_out)
+            sp.z = [z]
+            if need_post:
+                sp.mu, sp.sigma = mu_out['posterior'], sig['posterior']
+            if need_prior:
+                sp.prior_mu, sp.prior_sigma = mu_out['prior'], sig['prior']
+        else:
+            sp.z = [b.new(B, 1, 1, zd, f32)]
+        if need_lik:
+            sp.logits = _probunet_likelihood(b, cfg, sp.z[0], sp.x)
+
+    # --- heads of the graph
+    sp.s_out = sp.s_out_sm = sp.sm_accum = sp.argmax = None
+    if need_lik:
+        nlev = len(sp.logits)
+        lp = _ptr_array([a.ptr for a in sp.logits])
+        pr.keep.append(lp)
+        if kind in ('train', 'eval') and cfg.xent_weight is not None:
+            dl = None
+            if want_grad:
+                for a in sp.logits[1:]:
+                    g = a.grad()
+                    pr.emit('phs_fill_f32', g.ptr, a.N * a.H * a.W * a.C, 0.0)
+                dl = _ptr_array([a.grad().ptr for a in sp.logits])
+                pr.keep.append(dl)
+                for a in sp.logits:
+                    a.mark_grad_written()
+            pr.emit('phs_xent_multiscale', lp, dl, sp.s.data_ptr(), B, H, W, nl, nlev, cfg.xent_weight / B,
+                    sp.losses.data_ptr())
+        if kind in ('sample', 'from_z', 'eval'):
+            sp.s_out = torch.empty((B, H, W, nl), dtype=torch.float32, device=device)
+            sp.s_out_sm = torch.empty((B, H, W, nl), dtype=torch.float32, device=device)
+            sp.sm_accum = torch.zeros((B, H, W, nl), dtype=torch.float32, device=device)
+            sp.argmax = torch.empty((B, H, W), dtype=torch.int64, device=device)
+            pr.emit('phs_aggregate_logits', lp, B, H, W, nl, nlev, sp.s_out.data_ptr(), sp.s_out_sm.data_ptr(),
+                    sp.sm_accum.data_ptr(), sp.argmax.data_ptr())
+    sp.n_fwd = len(pr.steps)
+    if want_grad:
+        b.emit_backward()
+    sp.conv_flop_fwd = b.n_conv_flop
+    return sp
+
+
+def _emit_latent(b, sp, l, hw, mu, spre, sig, z, gen_mode, need_post, need_prior, gap, mu_out=None):
+    """softplus + reparameterisation + KL for one level (posteriors.py:105-108,125-128; phiseg_model.py:210-226,265-287)."""
+    cfg, pr, B, zd = b.cfg, b.prog, b.B, b.cfg.zdim0
+    q = 'posterior' if need_post else None
+    p = 'prior' if need_prior else None
+    w_l = float(4 ** l) if cfg.exponential_weighting else 1.0
+    want_kl = bool(q and p and cfg.KL_weight is not None)
+    kl_ptr = sp.losses.data_ptr() + 4 * (cfg.L + l) if want_kl else None
+    g = lambda d, n: d[n][l].ptr if n else None
+    pr.emit('phs_latent_fwd', g(mu, q), g(spre, q), g(mu, p), g(spre, p), sp.eps[l].data_ptr(), B, hw, zd, gap,
+            int(gen_mode), g(mu_out, q) if gap else None, g(sig, q), g(mu_out, p) if gap else None, g(sig, p), z.ptr,
+            kl_ptr, w_l / B)
+    if b.want_grad:
+        def bwd():
+            dz = z.grad().ptr if z.grad_written() else None
+            klw = (cfg.KL_weight * w_l / B) if want_kl else 0.0
+            outs = [mu['posterior'][l], spre['posterior'][l], mu['prior'][l], spre['prior'][l]]
+            mq = (mu_out if gap else mu)['posterior'][l]
+            mp = (mu_out if gap else mu)['prior'][l]
+            pr.emit('phs_latent_bwd', dz, mq.ptr, spre['posterior'][l].ptr, sig['posterior'][l].ptr, mp.ptr,
+                    spre['prior'][l].ptr, sig['prior'][l].ptr, sp.eps[l].data_ptr(), B, hw, zd, gap, klw,
+                    *[o.grad().ptr for o in outs])
+            for o in outs:
+                o.mark_grad_written()
+        b.tape.append(bwd)
+
+
+def _phiseg_likelihood(b, cfg, z):
+    """likelihoods.phiseg (likelihoods.py:162-223).  Returns native-resolution head outputs (the nearest-neighbour
+    resize of :221 is folded into the loss / aggregation kernels)."""
+    nc, Lv, R = cfg.nc, cfg.L, cfg.R
+    d = R - Lv
+    pr = b.prog
+    B, H, W = b.B, cfg.H, cfg.W
+    post_z, post_c = [None] * Lv, [None] * Lv
+    cat = [None] * Lv
+    for i in range(Lv):
+        h = b.conv(z[i], 'likelihood/z%d_post_1' % i, 3, nc[i])
+        h = b.conv(h, 'likelihood/z%d_post_2' % i, 3, nc[i])
+        for t in range(d):
+            h = b.up(h)
+            out = None
+            if t == d - 1 and i < Lv - 1:
+                cat[i] = Buf(pr, B, h.H, h.W, 2 * nc[i], b.adt)
+                out = cat[i].act(0, nc[i])
+            h = b.conv(h, 'likelihood/preups_%d/z%d_post' % (i, t), 3, nc[i], out=out)
+        post_z[i] = h
+    post_c[Lv - 1] = post_z[Lv - 1]
+    for i in reversed(range(Lv - 1)):
+        u = b.up(post_c[i + 1])
+        if d == 0:      # no pre-upsampling: the concat buffer was not created above
+            cat[i] = Buf(pr, B, u.H, u.W, 2 * nc[i], b.adt)
+            pr.emit('phs_copy_cast', post_z[i].desc(), cat[i].act(0, nc[i]).desc())
+            raise NotImplementedError('resolution_levels == latent_levels')
+        b.conv(u, 'likelihood/post_z%d_ups_c' % (i + 1), 3, nc[i], out=cat[i].act(nc[i], nc[i]))
+        h = b.conv(cat[i].act(), 'likelihood/post_c_%d_1' % i, 3, nc[i + d])
+        post_c[i] = b.conv(h, 'likelihood/post_c_%d_2' % i, 3, nc[i + d])
+    return [b.conv(post_c[i], 'likelihood/y_lvl%d' % i, 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32)
+            for i in range(Lv)]
+
+
+def _probunet_likelihood(b, cfg, z, x):
+    """likelihoods.prob_unet2D (likelihoods.py:81-159)."""
+    nc, R, zd = cfg.nc, cfg.R, cfg.zdim0
+    pr = b.prog
+    B, H, W = b.B, cfg.H, cfg.W
+    enc = []
+    cats = {}
+    h = x
+    for i in range(R):
+        if i > 0:
+            h = b.pool(h)
+        h = b.conv(h, 'likelihood/encoder/conv_%d_1' % i, 3, nc[i], need_dx=i > 0)
+        h = b.conv(h, 'likelihood/encoder/conv_%d_2' % i, 3, nc[i])
+        out = None
+        if i < R - 1:
+            # decoder stage jj = R-2-i concatenates [up(prev) | enc[i]] (crop_and_concat, layers.py:586-622)
+            prev_c = nc[min(i + 2, R - 1)]       # channels of up(previous decoder stage / enc[R-1])
+            cats[i] = Buf(pr, B, H >> i, W >> i, prev_c + nc[i], b.adt)
+            out = cats[i].act(prev_c, nc[i])
+        h = b.conv(h, 'likelihood/encoder/conv_%d_3' % i, 3, nc[i], out=out)
+        enc.append(h)
+    for jj in range(R - 1):
+        ii = R - jj - 1
+        cb = cats[ii - 1]
+        b.up(h, out=cb.act(0, h.C))
+        h = cb.act()
+        for t in (1, 2, 3):
+            out = None
+            if jj == R - 2 and t == 3:
+                rc = Buf(pr, B, H, W, nc[ii] + zd, b.adt)
+                out = rc.act(0, nc[ii])
+            h = b.conv(h, 'likelihood/decoder/conv_%d_%d' % (jj, t), 3, nc[ii], out=out)
+    zs = rc.act(h.C, zd)
+    pr.emit('phs_broadcast_z', z.ptr, zs.desc())          # tf.tile of z over H x W (likelihoods.py:147-151)
+    if b.want_grad:
+        def bwd():
+            pr.emit('phs_broadcast_z_bwd', zs.grad().desc(), z.grad().ptr, int(z.grad_written()))
+            z.mark_grad_written()
+        b.tape.append(bwd)
+    h = rc.act()
+    for t in range(3):
+        h = b.conv(h, 'likelihood/recomb_%d' % t, 1, nc[0])
+    return [b.conv(h, 'likelihood/prediction', 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32)]

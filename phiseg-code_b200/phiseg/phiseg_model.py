@@ -1,0 +1,517 @@
+"""B200-native counterpart of phiseg/phiseg_model.py::phiseg (reference lines cited per method).
+
+Same constructor argument (an experiment module), same method names, numpy in / numpy out.  Differences, all
+deliberate and listed in DESIGN.md: `training_step` and `generate_samples` exist as first-class methods (the
+reference only has the loop body phiseg_model.py:193-197 and the broken :478-481); the unseeded tf.random_normal
+draws can be replaced by injected `eps` so runs are reproducible; the BN moving-average double update of
+phiseg_model.py:135-141 is not reproduced.
+"""
+import logging
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from .. import engine as E
+from .. import lib as L
+from .. import parallel
+from ..tf_compat import optimizer_kind
+from ..tfwrapper.normalisation import norm_kind
+
+logging.basicConfig(level=logging.INFO, format='%(asctime)s %(message)s')
+
+
+def find_floor_in_list(keys, value):
+    """utils.py:70-84: largest key <= value (learning-rate schedule lookup, phiseg_model.py:189-190)."""
+    ks = sorted(keys)
+    best = None
+    for k in ks:
+        if k <= value:
+            best = k
+    if best is None:
+        raise ValueError('no schedule entry at or below step %d' % value)
+    return best
+
+
+def net_config_from_experiment(exp, mode):
+    """Reads the attributes phiseg_model.py:20-141 reads from exp_config."""
+    archs = {getattr(exp.posterior, 'arch', None), getattr(exp.prior, 'arch', None),
+             getattr(exp.likelihood, 'arch', None)}
+    if len(archs) != 1 or None in archs:
+        raise ValueError('posterior/prior/likelihood must name one architecture, got %r' % (archs,))
+    arch = archs.pop()
+    if arch not in ('phiseg', 'probunet'):
+        raise NotImplementedError('architecture %r is outside the B200 hot path (phiseg and prob_unet2D are built)' % arch)
+
+    def opt(name):
+        return getattr(exp, name) if hasattr(exp, name) and getattr(exp, name) is not None else None
+
+    return E.NetConfig(arch=arch, image_size=tuple(exp.image_size), nlabels=exp.nlabels, zdim0=exp.zdim0, n0=exp.n0,
+                       resolution_levels=exp.resolution_levels, latent_levels=exp.latent_levels,
+                       norm=norm_kind(exp.layer_norm), KL_weight=opt('KL_divergence_loss_weight'),
+                       xent_weight=opt('residual_multinoulli_loss_weight'),
+                       exponential_weighting=getattr(exp, 'exponential_weighting', True),
+                       weight_decay=opt('weight_decay_weight'), optimizer=optimizer_kind(exp.optimizer), mode=mode)
+
+
+class phiseg():
+
+    def __init__(self, exp_config, mode=None, device=None, use_cuda_graph=True, seed=1234):
+        """mode: 'parity' (fp32 CUDA-core kernels) or 'fast' (bf16 tcgen05 tensor-core kernels, fp32 accumulate and
+        fp32 normalisation statistics / losses / optimizer).  Default: exp_config.compute_mode if present, else 'fast'."""
+        self.exp_config = exp_config
+        if not torch.cuda.is_available():
+            raise RuntimeError('phiseg-code_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.lib = L.load()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        mode = mode or getattr(exp_config, 'compute_mode', 'fast')
+        self.cfg = net_config_from_experiment(exp_config, mode)
+        self.params = E.Params(self.cfg, self.device)
+        self.params.init(seed)
+        self.use_cuda_graph = use_cuda_graph
+        self._progs = {}
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(seed)
+        self._hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.loss_dict = {}
+        self.loss_tot = None
+        self.log_dir = None
+        self.gpu_launches = 0
+        self.world = 1
+        self.rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size()
+            self.rank = torch.distributed.get_rank()
+            if self.world > 1:
+                # identical replicas: rank 0's initial weights everywhere
+                torch.distributed.broadcast(self.params.p, 0)
+                torch.distributed.broadcast(self.params.state, 0)
+                self.params.refresh_shadow()
+
+    # ---------------------------------------------------------------------------------------------------
+    # programs
+    # ---------------------------------------------------------------------------------------------------
+    def _program(self, kind, B):
+        key = (kind, B)
+        sp = self._progs.get(key)
+        if sp is None:
+            sp = E.build_program(self.cfg, self.params, B, kind, self.device)
+            sp.graph = None
+            sp.runs = 0
+            sp.h_x = torch.zeros((B, self.cfg.H, self.cfg.W, self.cfg.Cx), dtype=torch.float32).pin_memory()
+            sp.h_s = torch.zeros((B, self.cfg.H, self.cfg.W), dtype=torch.uint8).pin_memory()
+            sp.h_losses = torch.zeros(sp.losses.numel(), dtype=torch.float32).pin_memory()
+            if kind == 'train':
+                self._append_optimizer(sp)
+            self._progs[key] = sp
+        return sp
+
+    def _append_optimizer(self, sp):
+        """Gradient zeroing goes in front of the backward launches; weight decay, the optimizer update and the bf16
+        shadow refresh go behind them (phiseg_model.py:134-141,290-300)."""
+        P, pr, cfg = self.params, sp.prog, self.cfg
+        P.ensure_slots()
+        steps = pr.steps
+        fwd, bwd = steps[:sp.n_fwd], steps[sp.n_fwd:]
+        pr.steps = []
+        pr.emit('phs_fill_f32', P.g.data_ptr(), P.n, 0.0)
+        zero = pr.steps
+        pr.steps = []
+        if cfg.weight_decay is not None:
+            for name, (off, shape, kind) in P.table.items():
+                if kind == 'W':
+                    n = int(np.prod(shape))
+                    pr.emit('phs_sumsq_f32', P.ptr(name), n, 0.5 * cfg.weight_decay, sp.losses.data_ptr() + 4 * (2 * cfg.L))
+                    pr.emit('phs_axpy_f32', P.ptr(name, 'g'), P.ptr(name), n, float(cfg.weight_decay))
+        wd = pr.steps
+        pr.steps = []
+        gs = 1.0 / self.world
+        if cfg.optimizer == 'adam':
+            pr.emit('phs_adam_step', P.p.data_ptr(), P.g.data_ptr(), P.slots[0].data_ptr(), P.slots[1].data_ptr(), P.n,
+                    0.0, self._hyper.data_ptr(), 0.9, 0.999, 1e-8, gs)
+        else:
+            pr.emit('phs_momentum_step', P.p.data_ptr(), P.g.data_ptr(), P.slots[0].data_ptr(), P.n, 0.0,
+                    self._hyper.data_ptr(), 0.9, gs)
+        if P.shadow is not None and P.prep_table.numel():
+            pr.emit('phs_weight_prep', P.p.data_ptr(), P.shadow.data_ptr(), P.prep_table.data_ptr(),
+                    P.prep_table.shape[0])
+        opt = pr.steps
+        sp.grad_steps = fwd + zero + bwd + wd           # produces losses and the local gradient
+        sp.opt_steps = opt                               # consumes the (all-reduced) gradient
+        pr.steps = sp.grad_steps + sp.opt_steps
+
+    def _launch(self, sp, steps, tag):
+        """Replay a launch list: eagerly the first time (loads modules, validates arguments), then from a CUDA
+        graph captured on the second call."""
+        pr = sp.prog
+        self.gpu_launches += len(steps)
+        if not self.use_cuda_graph:
+            pr.run_eager(steps)
+            return
+        graphs = sp.__dict__.setdefault('graphs', {})
+        seen = sp.__dict__.setdefault('seen', {})
+        if tag in graphs:
+            graphs[tag].replay()
+            return
+        if seen.get(tag, 0) >= 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pr.run_eager(steps)
+            graphs[tag] = g
+            g.replay()
+            return
+        seen[tag] = seen.get(tag, 0) + 1
+        pr.run_eager(steps)
+
+    # ---------------------------------------------------------------------------------------------------
+    # input staging
+    # ---------------------------------------------------------------------------------------------------
+    def _stage_x(self, sp, x_in):
+        x = np.asarray(x_in, dtype=np.float32)
+        if x.shape != tuple(sp.h_x.shape):
+            raise ValueError('x has shape %s, expected %s' % (x.shape, tuple(sp.h_x.shape)))
+        sp.h_x.numpy()[...] = x
+        sp.x.buf.t.copy_(sp.h_x, non_blocking=True)
+        return sp.h_x.numel() * 4
+
+    def _stage_s(self, sp, s_in):
+        s = np.asarray(s_in)
+        if s.shape != tuple(sp.h_s.shape):
+            raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
+        if s.size and (s.min() < 0 or s.max() >= self.cfg.nlabels):
+            raise ValueError('labels must lie in [0, %d)' % self.cfg.nlabels)
+        sp.h_s.numpy()[...] = s.astype(np.uint8)
+        sp.s.copy_(sp.h_s, non_blocking=True)
+        return sp.h_s.numel()
+
+    def _draw_eps(self, sp, eps=None):
+        if eps is None:
+            for e in sp.eps:
+                e.normal_(generator=self._gen)
+        else:
+            if len(eps) != len(sp.eps):
+                raise ValueError('eps must have one entry per latent level (%d)' % len(sp.eps))
+            for e, v in zip(sp.eps, eps):
+                v = torch.as_tensor(np.asarray(v, dtype=np.float32)) if not torch.is_tensor(v) else v
+                e.copy_(v.reshape(e.shape).to(self.device, torch.float32))
+
+    # ---------------------------------------------------------------------------------------------------
+    # training
+    # ---------------------------------------------------------------------------------------------------
+    def _lr_for_step(self, step):
+        sched = self.exp_config.lr_schedule_dict
+        return sched[find_floor_in_list(sched.keys(), step)]
+
+    def _device_step(self, sp, lr):
+        """loss, gradients, (all-reduce,) optimizer on inputs already resident in sp.x / sp.s / sp.eps."""
+        P = self.params
+        t = P.step + 1
+        if self.cfg.optimizer == 'adam':
+            # tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+            lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        else:
+            lr_t = lr
+        self._hyper_host[0] = lr_t
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        if self.world > 1:
+            self._launch(sp, sp.grad_steps, 'grad')
+            parallel.allreduce_sum_(P.g)                # one all-reduce over the flat gradient buffer (NCCL/NVLink)
+            self._launch(sp, sp.opt_steps, 'opt')
+        else:
+            self._launch(sp, sp.prog.steps, 'step')
+        P.step = t
+
+    def _read_losses(self, sp):
+        sp.h_losses.copy_(sp.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        v = sp.h_losses.numpy()
+        cfg = self.cfg
+        ld = {}
+        tot = 0.0
+        if cfg.xent_weight is not None:
+            for l in range(cfg.L):
+                ld['residual_multinoulli_loss_lvl%d' % l] = float(v[l]) / cfg.xent_weight
+                tot += float(v[l])
+        if cfg.KL_weight is not None:
+            for l in range(cfg.L):
+                ld['KL_divergence_loss_lvl%d' % l] = float(v[cfg.L + l])
+                tot += cfg.KL_weight * float(v[cfg.L + l])
+        if cfg.weight_decay is not None:
+            ld['weight_decay'] = float(v[2 * cfg.L])
+            tot += float(v[2 * cfg.L])
+        ld['total_loss'] = tot
+        self.loss_dict = ld
+        self.loss_tot = tot
+        return tot
+
+    def training_step(self, x_b, s_b, lr=None, eps=None):
+        """One iteration of the hot loop (phiseg_model.py:186-197): feed a batch, run forward, ELBO, backward and the
+        optimizer, return loss_tot.  x_b [B,H,W,C] float32, s_b [B,H,W] uint8 (host arrays)."""
+        B = int(np.shape(x_b)[0])
+        sp = self._program('train', B)
+        if lr is None:
+            lr = self._lr_for_step(self.params.step)
+        self.h2d_bytes = self._stage_x(sp, x_b) + self._stage_s(sp, s_b)
+        self._draw_eps(sp, eps)
+        self._device_step(sp, lr)
+        self.d2h_bytes = sp.h_losses.numel() * 4
+        return self._read_losses(sp)
+
+    def train(self, data):
+        """phiseg_model.py:166-207 without TensorBoard: lr schedule lookup, next_batch, training_step, periodic
+        validation losses and checkpoints."""
+        exp = self.exp_config
+        self._setup_log_dir_and_continue_mode()
+        self.best_loss = np.inf
+        for step in range(self.init_step, exp.num_iter):
+            lr = self._lr_for_step(step)
+            x_b, s_b = data.train.next_batch(exp.batch_size)
+            loss = self.training_step(x_b, s_b, lr)
+            if step % exp.tensorboard_update_frequency == 0:
+                logging.info('step %d  loss %.4f  lr %g' % (step, loss, lr))
+            if step % exp.validation_frequency == 0:
+                self._do_validation(data, step)
+
+    def _do_validation(self, data, step):
+        """Reduced form of phiseg_model.py:530-701: checkpoint + validation ELBO with training=False + best-loss
+        tracking (GED/NCC/Dice metrics are a 'next' row)."""
+        self.save_weights(self.log_dir, 'model.ckpt-%d' % step)
+        if hasattr(data, 'validation'):
+            x_b, s_b = data.validation.next_batch(self.exp_config.batch_size)
+            val = self.evaluate_losses(x_b, s_b)
+            logging.info('validation  step %d  loss %.4f' % (step, val['total_loss']))
+            if val['total_loss'] < self.best_loss:
+                self.best_loss = val['total_loss']
+                self.save_weights(self.log_dir, 'model_best_loss.ckpt-%d' % step)
+
+    def evaluate_losses(self, x_b, s_b, eps=None):
+        """loss_dict with training=False (phiseg_model.py:537-549)."""
+        B = int(np.shape(x_b)[0])
+        sp = self._program('eval', B)
+        self._stage_x(sp, x_b)
+        self._stage_s(sp, s_b)
+        self._draw_eps(sp, eps)
+        self._launch(sp, sp.prog.steps, 'fwd')
+        self._read_losses(sp)
+        return dict(self.loss_dict)
+
+    # ---------------------------------------------------------------------------------------------------
+    # sampling / prediction (phiseg_model.py:313-502)
+    # ---------------------------------------------------------------------------------------------------
+    def _sample_once(self, sp, eps=None):
+        self._draw_eps(sp, eps)
+        self._launch(sp, sp.prog.steps, 'fwd')
+
+    def _np(self, t):
+        return t.detach().cpu().numpy()
+
+    def predict(self, x_in, num_samples=50, return_softmax=False):
+        """phiseg_model.py:337-353: softmax of the summed level outputs averaged over num_samples prior draws, argmax."""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('sample', B)
+        self._stage_x(sp, x_in)
+        sp.sm_accum.zero_()
+        for _ in range(num_samples):
+            self._sample_once(sp)
+        st = torch.cuda.current_stream().cuda_stream
+        npix = B * self.cfg.H * self.cfg.W
+        L.check(self.lib.phs_argmax_f32(sp.sm_accum.data_ptr(), npix, self.cfg.nlabels, sp.argmax.data_ptr(), st), 'phs_argmax_f32')
+        self.gpu_launches += 1
+        if return_softmax:
+            return self._np(sp.argmax), self._np(sp.sm_accum) / num_samples
+        return self._np(sp.argmax)
+
+    def predict_segmentation_sample(self, x_in, return_softmax=False, eps=None):
+        """phiseg_model.py:356-364"""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('sample', B)
+        self._stage_x(sp, x_in)
+        self._sample_once(sp, eps)
+        if return_softmax:
+            return self._np(sp.s_out_sm)
+        return self._np(sp.argmax)
+
+    def _levels_full_res(self, sp):
+        """tf.image.resize_images(..., NEAREST_NEIGHBOR) of each level's head output (likelihoods.py:221): pure
+        replication, done on the host copy."""
+        out = []
+        for a in sp.logits:
+            y = self._np(a.tensor().float())
+            f = self.cfg.H // y.shape[1]
+            out.append(np.repeat(np.repeat(y, f, axis=1), f, axis=2) if f > 1 else y)
+        return out
+
+    def predict_segmentation_sample_levels(self, x_in, return_softmax=False, eps=None):
+        """phiseg_model.py:367-375"""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('sample', B)
+        self._stage_x(sp, x_in)
+        self._sample_once(sp, eps)
+        lv = self._levels_full_res(sp)
+        if return_softmax:
+            res = []
+            for y in lv:
+                e = np.exp(y - y.max(axis=-1, keepdims=True))
+                res.append(e / e.sum(axis=-1, keepdims=True))
+            return res
+        return lv
+
+    def generate_prior_samples(self, x_in, return_params=False, eps=None):
+        """phiseg_model.py:325-334.  Unlike the reference (three sess.run calls, three different noise draws) the
+        returned mu / sigma belong to the returned z."""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('sample', B)
+        self._stage_x(sp, x_in)
+        self._sample_once(sp, eps)
+        shp = self.cfg.latent_shapes(B)
+        z = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.z, shp)]
+        if return_params:
+            mu = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.prior_mu, shp)]
+            sg = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.prior_sigma, shp)]
+            return z, mu, sg
+        return z
+
+    def generate_posterior_samples(self, x_in, s_in, return_params=False, eps=None):
+        """phiseg_model.py:484-495"""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('posterior', B)
+        self._stage_x(sp, x_in)
+        self._stage_s(sp, s_in)
+        self._sample_once(sp, eps)
+        shp = self.cfg.latent_shapes(B)
+        z = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.z, shp)]
+        if return_params:
+            mu = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.mu, shp)]
+            sg = [self._np(a.tensor()).reshape(s) for a, s in zip(sp.sigma, shp)]
+            return z, mu, sg
+        return z
+
+    def generate_samples_from_z(self, z_list, x_in, output_all_levels=False):
+        """phiseg_model.py:313-322: decode given latents with training=False."""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('from_z', B)
+        self._stage_x(sp, x_in)
+        if len(z_list) != len(sp.z):
+            raise ValueError('z_list must have %d entries' % len(sp.z))
+        for a, z in zip(sp.z, z_list):
+            zt = torch.as_tensor(np.asarray(z, dtype=np.float32)).reshape(a.buf.t.shape)
+            a.buf.t.copy_(zt.to(self.device))
+        self._launch(sp, sp.prog.steps, 'fwd')
+        if output_all_levels:
+            return self._levels_full_res(sp)
+        return self._np(sp.s_out)
+
+    def generate_samples_from_prior(self, x_in, output_all_levels=False):
+        """Intent of phiseg_model.py:478-481 (the reference passes output_all_levels as x_in by mistake)."""
+        z = self.generate_prior_samples(x_in)
+        return self.generate_samples_from_z(z, x_in, output_all_levels)
+
+    def generate_samples(self, x_in, num_samples, output_all_levels=False):
+        """num_samples segmentation-logit samples per image: [num_samples, B, H, W, nlabels]
+        (or a list over levels of such arrays)."""
+        outs = [self.generate_samples_from_prior(x_in, output_all_levels) for _ in range(num_samples)]
+        if output_all_levels:
+            return [np.stack([o[l] for o in outs]) for l in range(len(outs[0]))]
+        return np.stack(outs)
+
+    def get_crossentropy_error_map(self, s_gt, x_in, num_samples=100):
+        """phiseg_model.py:433-446: mean over samples of the per-pixel cross entropy of s_out_eval."""
+        s = np.asarray(s_gt).astype(np.int64)
+        acc = 0.0
+        for _ in range(num_samples):
+            sm = self.predict_segmentation_sample(x_in, return_softmax=True)
+            p = np.take_along_axis(sm, s[..., None], axis=-1)[..., 0]
+            acc = acc - np.log(np.maximum(p, 1e-38))
+        return acc / num_samples
+
+    def predict_mean_variance_and_error_maps(self, s_gt, x_in, num_samples):
+        """phiseg_model.py:449-475"""
+        s = np.asarray(s_gt).astype(np.int64)
+        segs, errs = [], []
+        for _ in range(num_samples):
+            sm = self.predict_segmentation_sample(x_in, return_softmax=True)
+            segs.append(sm)
+            errs.append(-np.log(np.maximum(np.take_along_axis(sm, s[..., None], axis=-1)[..., 0], 1e-38)))
+        segm_arr = np.squeeze(np.asarray(segs))
+        vars_ = np.mean(np.std(segm_arr, axis=0), axis=-1)
+        means = np.argmax(np.mean(segm_arr, 0), axis=-1)
+        return means, vars_, np.mean(np.squeeze(np.asarray(errs)), axis=0)
+
+    # ---------------------------------------------------------------------------------------------------
+    # weights / checkpoints (phiseg_model.py:144-148,505-525,821-845)
+    # ---------------------------------------------------------------------------------------------------
+    def get_weights(self):
+        """{TF variable name: numpy array} (names as produced by the reference's variable scopes)."""
+        return {k: v.numpy() for k, v in self.params.state_dict().items()}
+
+    def set_weights(self, weights, strict=True):
+        self.params.load_state_dict(weights, strict)
+
+    def save_weights(self, log_dir, name='model.ckpt'):
+        os.makedirs(log_dir, exist_ok=True)
+        path = os.path.join(log_dir, name + '.npz')
+        extra = {'__global_step__': np.asarray(self.params.step)}
+        if self.params.slots is not None:
+            for i, sl in enumerate(self.params.slots):
+                extra['__slot%d__' % i] = sl.detach().cpu().numpy()
+        np.savez(path, **self.get_weights(), **extra)
+        return path
+
+    def load_weights(self, log_dir=None, type='latest', **kwargs):
+        """phiseg_model.py:505-525"""
+        if not log_dir:
+            log_dir = self.log_dir
+        prefix = {'latest': 'model.ckpt', 'best_dice': 'model_best_dice.ckpt', 'best_loss': 'model_best_loss.ckpt',
+                  'best_ged': 'model_best_ged.ckpt', 'best_ncc': 'model_best_ncc.ckpt'}
+        if type == 'iter':
+            assert 'iteration' in kwargs, "argument 'iteration' must be provided for type='iter'"
+            path = os.path.join(log_dir, 'model.ckpt-%d.npz' % kwargs['iteration'])
+        elif type in prefix:
+            path = _latest_checkpoint(log_dir, prefix[type])
+        else:
+            raise ValueError('Argument type=%s is unknown. type can be latest/iter.' % type)
+        if path is None or not os.path.exists(path):
+            raise FileNotFoundError('no checkpoint of type %s in %s' % (type, log_dir))
+        data = np.load(path)
+        self.params.load_state_dict({k: data[k] for k in data.files if not k.startswith('__')})
+        if '__global_step__' in data.files:
+            self.params.step = int(data['__global_step__'])
+        if '__slot0__' in data.files:
+            self.params.ensure_slots()
+            for i, sl in enumerate(self.params.slots):
+                sl.copy_(torch.as_tensor(data['__slot%d__' % i]).to(self.device))
+        return path
+
+    def _setup_log_dir_and_continue_mode(self):
+        """phiseg_model.py:821-845: resume from <log_dir> if it holds a checkpoint."""
+        root = getattr(self.exp_config, 'log_root', os.environ.get('PHISEG_LOG_ROOT', './logs'))
+        self.log_dir = os.path.join(root, self.exp_config.log_dir_name, self.exp_config.experiment_name)
+        os.makedirs(self.log_dir, exist_ok=True)
+        self.init_step = 0
+        self.continue_run = False
+        path = _latest_checkpoint(self.log_dir, 'model.ckpt')
+        if path is not None:
+            self.load_weights(self.log_dir, 'latest')
+            self.init_step = self.params.step
+            self.continue_run = True
+            logging.info('continuing from %s (step %d)' % (path, self.init_step))
+
+
+def _latest_checkpoint(log_dir, prefix):
+    """tfwrapper/utils.py:189-210: highest-iteration checkpoint with the given prefix."""
+    best, best_it = None, -1
+    if not os.path.isdir(log_dir):
+        return None
+    for f in os.listdir(log_dir):
+        if f.startswith(prefix) and f.endswith('.npz'):
+            mid = f[len(prefix):-4]
+            it = int(mid[1:]) if mid.startswith('-') and mid[1:].isdigit() else 0
+            if it > best_it:
+                best, best_it = os.path.join(log_dir, f), it
+    return best
