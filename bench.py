@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""Benchmark of the PHiSeg hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config NAME] [--batch B]
+
+A "step" is one training iteration (forward, ELBO, hand-written backward, Adam) of phiseg_7_5 on a synthetic LIDC-shaped
+batch (128x128x1 float32 images, uint8 masks), B=64 images per GPU (BASELINE.json configs[1]); with N>1 ranks the batch
+is sharded data-parallel, B=64 per rank (weak scaling, configs[3] at N=8) and the flat gradient buffer is all-reduced
+once per step over NCCL.
+
+  value     images/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e       images/s through phiseg.training_step(x_host, s_host): pinned-host -> device copies of the batch and the
+            device -> host read of the losses inside the timed region
+  roofline  algorithmic conv FLOPs of the step (fwd + dgrad + wgrad of the live convolutions) divided by
+            the device time of the step, against the measured sustained bf16 tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference
+            the PyTorch-CPU oracle restatement of the reference graph (TF 1.12 cannot be installed: Python 3.12, no
+            network) on the host cores, on a bounded sample (B=12, the reference's own batch size)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (experiment, batch per GPU, image size, nlabels)
+    'phiseg_7_5': ('phiseg_7_5', 64, 128, 2),
+    'phiseg_7_5_gn': ('phiseg_7_5_gn', 64, 128, 2),
+    'probunet': ('probunet', 64, 128, 2),
+    'phiseg_7_5_256': ('phiseg_7_5_256', 32, 256, 4),
+}
+CPU_BATCH = 12   # phiseg/experiments/phiseg_7_5.py:38
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get('bf16_tflops_sustained', 1395.6), d.get('hbm_gbs', 6445.0), 'measured (MEASURED_PEAKS.json, sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [c.strip() for c in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'power_w_max': max(pw), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def run_cpu_oracle(steps, warmup, batch=CPU_BATCH, size=128):
+    """The CPU stand-in for the reference's TF-1.12 path: one full training step of the oracle (forward, ELBO, autograd
+    backward, TF-form Adam) per iteration, all host threads."""
+    import torch
+    from __graft_entry__ import load_oracle
+    o = load_oracle()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = o.Oracle('phiseg', image_size=(size, size, 1), norm='batch_norm', dtype=torch.float32)
+    orc.init_params(seed=1234)
+    x, s = o.synthetic_batch(batch, size, size, 2, seed=1235)
+    eps = [torch.tensor(e) for e in o.synthetic_eps(orc.latent_shapes(batch), seed=1234)]
+    xt, st = torch.tensor(x), torch.tensor(s)
+    for _ in range(warmup):
+        orc.train_step(xt, st, eps, 1e-3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.train_step(xt, st, eps, 1e-3)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='phiseg_7_5', choices=sorted(CONFIGS))
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the config\'s)')
+    ap.add_argument('--mode', default='fast', choices=['fast', 'parity'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    metric = 'LIDC 128x128 training images/sec'
+    exp_name, batch, size, nlabels = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 3))
+        warm = max(1, min(args.warmup, 1))
+        ips, sps, cores = run_cpu_oracle(steps, warm)
+        line = {'impl': 'reference', 'metric': metric, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus,
+                'steps': steps, 'warmup': warm, 'ms_per_step': sps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'phiseg_7_5 LIDC 128x128, batch=%d, CPU oracle restatement of the TF-1.12 graph '
+                                       '(TF 1.12 not installable: Python 3.12, no network)' % CPU_BATCH},
+                'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                 'sample': '%d training steps of batch %d at 128x128 (after %d warm-up)' % (steps, CPU_BATCH, warm)},
+                'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    from __graft_entry__ import load_package, load_oracle
+    load_package()
+    import importlib
+    parallel = importlib.import_module('phiseg_code_b200.parallel')
+    pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
+    ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
+    rank, world, local = parallel.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+
+    exp = ex.load_experiment(ex.experiment_path(exp_name))
+    model = pm.phiseg(exp, mode=args.mode, use_cuda_graph=not args.no_graph)
+    o = load_oracle()   # only its synthetic-input generator and (rank 0) the cpu_baseline leg are used here
+    x, s = o.synthetic_batch(batch, size, size, nlabels, seed=1235 + rank)
+    lr = 1e-3
+
+    # ---- device-resident throughput ---------------------------------------------------------------------
+    sp = model._program('train', batch)
+    model._stage_x(sp, x)
+    model._stage_s(sp, s)
+    torch.cuda.synchronize()
+
+    def dev_step():
+        model._draw_eps(sp)
+        model._device_step(sp, lr)
+
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = model.gpu_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        dev_step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    dt_dev = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    launches = model.gpu_launches - launches0
+    model._read_losses(sp)
+    loss_dev = model.loss_tot
+
+    # ---- end to end through the public API ----------------------------------------------------------------
+    for _ in range(2):
+        model.training_step(x, s, lr)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = model.training_step(x, s, lr)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    dt_e2e = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        return 0
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    flop_step = 3.0 * sp.conv_flop_fwd          # fwd + dgrad + wgrad of the live convolutions (per rank)
+    achieved = flop_step * args.steps / dt_dev / 1e12
+    line = {
+        'metric': metric, 'value': world * batch * args.steps / dt_dev, 'unit': 'images/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dt_dev / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16' if args.mode == 'fast' else 'f32', 'data': 'synthetic',
+        'config': {'workload': '%s LIDC %dx%d %s, batch=%d per GPU, %d x B200 (training step: fwd + ELBO + bwd + Adam)'
+                               % (exp_name, size, size, 'bf16' if args.mode == 'fast' else 'f32', batch, world),
+                   'global_batch': world * batch, 'norm': model.cfg.norm,
+                   'parallelism': 'dp%d' % world if world > 1 else 'single',
+                   'cuda_graph': not args.no_graph,
+                   'l2': 'per-step working set (activations + gradients, > 2 GB) exceeds the 126 MB L2; no explicit flush'},
+        'gpu_launches': launches,
+        'loss': loss_dev,
+        'clocks': clk,
+        'e2e': {'value': world * batch * args.steps / dt_e2e, 'unit': 'images/s',
+                'h2d_bytes_per_step': int(model.h2d_bytes), 'd2h_bytes_per_step': int(model.d2h_bytes),
+                'ms_per_step': dt_e2e / args.steps * 1e3},
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak_tf, 'traffic': None,
+                     'what': 'conv stack of the training step (tcgen05 conv_tc_kernel + wgrad_tc_kernel launches): '
+                             '%.2f algorithmic GFLOP/image x %d images / step time; peak = %s'
+                             % (flop_step / batch / 1e9, batch, peak_src)},
+    }
+    if world == 1 and not args.no_cpu:
+        ips, sps, cores = run_cpu_oracle(2, 1)
+        line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': '2 training steps of batch %d at 128x128 (after 1 warm-up), PyTorch-CPU oracle '
+                                          'stand-in for the TF-1.12 CPU path' % CPU_BATCH}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

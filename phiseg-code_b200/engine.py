@@ -158,7 +158,7 @@ def he_normal(gen, shape):
 
 def tc_eligible(k, cin, cout):
     """Shapes the tcgen05 implicit-GEMM kernels take (conv_tc.cu)."""
-    return cin % 32 == 0 and cout % 16 == 0 and 16 <= cout <= 256
+    return cin % 32 == 0 and cout % 32 == 0 and cout <= 256
 
 
 class Params:
