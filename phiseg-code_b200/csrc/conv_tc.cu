@@ -135,7 +135,7 @@ int num_sms() {
 // ------------------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------------------
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 16;
 
 struct ConvParams {
   int N, H, W, Cin, Cout;

@@ -283,6 +283,7 @@ class Buf:
         f = torch.zeros if zero else torch.empty
         self.t = f((N, H, W, ld), dtype=_TORCH_DT[dtype], device=prog.device)
         prog.bytes += self.t.numel() * _ES[dtype]
+        prog.keep.append(self.t)     # launches hold raw pointers: the program owns every buffer it addresses
         self.gbuf = None
         self.gw = []          # channel ranges of the gradient already written by an adjoint launch
 
