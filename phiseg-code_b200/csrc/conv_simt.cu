@@ -209,8 +209,17 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const TD* __restrict__ d
 
 }  // namespace
 
+int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
+                   int accumulate, cudaStream_t st);
+int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ksize, cudaStream_t st);
+
 int conv2d_simt(const phs_tensor* x, const float* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
                 int accumulate, cudaStream_t st) {
+  {
+    // tiny channel count on one side: dedicated streaming kernels (small_conv.cu)
+    int r = small_conv_try(x, w, bias, y, ksize, dgrad, accumulate, st);
+    if (r != 0) return r == 1 ? 0 : r;
+  }
   ConvGeom g;
   g.N = x->N; g.H = x->H; g.W = x->W;
   g.Cin = x->C; g.Cout = y->C;
@@ -249,6 +258,9 @@ int conv2d_wgrad_simt(const phs_tensor* x, const phs_tensor* dy, float* dw, floa
     cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.K * g.Cout, st);
     if (db) cudaMemsetAsync(db, 0, sizeof(float) * g.Cout, st);
   }
+  int rc = small_wgrad_try(x, dy, dw, ksize, st);
+  if (rc != 0 && rc != 1) return rc;
+  const bool handled = rc == 1;
   int gx = (g.K + 63) / 64, gy = (g.Cout + 63) / 64;
   int64_t splits = (148 * 4 + gx * gy - 1) / (gx * gy);
   int64_t max_splits = ceil_div64(g.M, 256);
@@ -257,7 +269,8 @@ int conv2d_wgrad_simt(const phs_tensor* x, const phs_tensor* dy, float* dw, floa
   int64_t mps = ceil_div64(ceil_div64(g.M, splits), 16) * 16;
   splits = ceil_div64(g.M, mps);
   dim3 grid(gx, gy, (unsigned)splits);
-  if (x->dtype == PHS_F32 && dy->dtype == PHS_F32)
+  if (handled) {
+  } else if (x->dtype == PHS_F32 && dy->dtype == PHS_F32)
     wgrad_simt_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x->ptr, (const float*)dy->ptr, dw, g, mps);
   else if (x->dtype == PHS_F32)
     wgrad_simt_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x->ptr, (const bf16*)dy->ptr, dw, g, mps);
@@ -265,7 +278,7 @@ int conv2d_wgrad_simt(const phs_tensor* x, const phs_tensor* dy, float* dw, floa
     wgrad_simt_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x->ptr, (const float*)dy->ptr, dw, g, mps);
   else
     wgrad_simt_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x->ptr, (const bf16*)dy->ptr, dw, g, mps);
-  int rc = phs_check_launch("conv2d_wgrad_simt");
+  rc = phs_check_launch("conv2d_wgrad_simt");
   if (rc) return rc;
   if (db) {
     PHS_REQUIRE(dy->C <= 256, "bias gradient: C=%d too large for the head kernel", dy->C);

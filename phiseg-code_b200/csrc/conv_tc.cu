@@ -16,16 +16,18 @@
 //   - both operands are MN-major in shared memory (channels contiguous), again plain TMA boxes of the NHWC tensors;
 //   - a CTA owns (tap, 128-channel block of Cin, a slice of the pixel range); partial sums are added to the fp32 HWIO
 //     gradient with vector red.global.add (split-K).
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
 #include "common.cuh"
 #include "tc_ptx.cuh"
-
-namespace {
+#include "tc_host.cuh"
 
 using namespace tc;
+
+namespace {
 
 // ------------------------------------------------------------------------------------------------------------
 // host: tensor maps
@@ -51,6 +53,8 @@ typedef std::tuple<const void*, int, int, int, int, int, int, int, int, int, int
 std::map<MapKey, CUtensorMap> g_maps;
 std::mutex g_maps_mu;
 
+}  // namespace
+
 // 4-D map over an NHWC bf16 channel slice: dims (C, W, H, N), box (bc, bw, bh, bn); swz_bytes = bc * 2 in {64, 128}
 int activation_map(const phs_tensor* t, int bc, int bw, int bh, int bn, CUtensorMap* out) {
   MapKey key(t->ptr, t->N, t->H, t->W, t->C, t->ld, bc, bw, bh, bn, 4);
@@ -75,9 +79,9 @@ int activation_map(const phs_tensor* t, int bc, int bw, int bh, int bn, CUtensor
   return 0;
 }
 
-// 2-D map over the K-major filter shadow [rows][K] bf16: box (bk, rows)
-int filter_map(const void* w, int K, int rows, int bk, CUtensorMap* out) {
-  MapKey key(w, K, rows, bk, 0, 0, 0, 0, 0, 0, 2);
+// 2-D map over the K-major filter shadow [rows][K] bf16: box (bk, box_rows)
+int filter_map_rows(const void* w, int K, int rows, int bk, int box_rows, CUtensorMap* out) {
+  MapKey key(w, K, rows, bk, box_rows, 0, 0, 0, 0, 0, 2);
   std::lock_guard<std::mutex> lk(g_maps_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
@@ -88,7 +92,7 @@ int filter_map(const void* w, int K, int rows, int bk, CUtensorMap* out) {
   PHS_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUtensorMapSwizzle swz = bk * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
@@ -97,6 +101,9 @@ int filter_map(const void* w, int K, int rows, int bk, CUtensorMap* out) {
   g_maps[key] = *out;
   return 0;
 }
+int filter_map(const void* w, int K, int rows, int bk, CUtensorMap* out) { return filter_map_rows(w, K, rows, bk, rows, out); }
+
+namespace {
 
 int next_pow2(int v) {
   int p = 1;
@@ -121,6 +128,8 @@ Brick make_brick(int N, int H, int W, int P) {
   return b;
 }
 
+}  // namespace
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -131,6 +140,8 @@ int num_sms() {
   }
   return n;
 }
+
+namespace {
 
 // ------------------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
@@ -459,22 +470,6 @@ __global__ void __launch_bounds__(256) bias_grad_bf16_kernel(const bf16* __restr
   }
 }
 
-bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
-
-// dynamic shared memory opt-in: 227 KB per CTA minus the kernel's static shared memory
-constexpr int SMEM_OPTIN = 227 * 1024 - 2048;
-template <typename K>
-int allow_big_smem(K kernel, bool* done) {
-  if (*done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN);
-  if (e != cudaSuccess) {
-    phs_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(e));
-    return (int)e;
-  }
-  *done = true;
-  return 0;
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -540,6 +535,16 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   return phs_check_launch("conv_tc_kernel");
 }
 
+bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
+int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
+
+static int bias_grad_tc(const phs_tensor* dy, float* db, cudaStream_t st) {
+  const int64_t M = (int64_t)dy->N * dy->H * dy->W;
+  int blocks = (int)(ceil_div64(M, 64) < 296 ? ceil_div64(M, 64) : 296);
+  bias_grad_bf16_kernel<<<dim3(blocks, (dy->C + 31) / 32), 256, 0, st>>>((const bf16*)dy->ptr, dy->ld, dy->C, M, db);
+  return phs_check_launch("bias_grad_bf16");
+}
+
 int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,
                     cudaStream_t st) {
   PHS_REQUIRE(x->dtype == PHS_BF16 && dy->dtype == PHS_BF16, "conv2d_wgrad_tc: x and dy must be bf16");
@@ -552,6 +557,11 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
   if (!accumulate) {
     cudaMemsetAsync(dw, 0, nw * sizeof(float), st);
     if (db) cudaMemsetAsync(db, 0, dy->C * sizeof(float), st);
+  }
+  if (wgrad_halo_eligible(x, dy, ksize) && !getenv("PHS_NO_HALO")) {
+    int rc = conv2d_wgrad_halo(x, dy, dw, st);
+    if (rc) return rc;
+    return db ? bias_grad_tc(dy, db, st) : 0;
   }
   WgradParams p;
   p.N = x->N; p.H = x->H; p.W = x->W; p.Cin = x->C; p.Cout = dy->C;
@@ -586,11 +596,5 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
   wgrad_tc_kernel<<<dim3(splits, items), 192, smem, st>>>(tmX, tmDY, p);
   rc = phs_check_launch("wgrad_tc_kernel");
   if (rc) return rc;
-  if (db) {
-    const int64_t M = (int64_t)x->N * x->H * x->W;
-    int blocks = (int)(ceil_div64(M, 64) < 296 ? ceil_div64(M, 64) : 296);
-    bias_grad_bf16_kernel<<<dim3(blocks, (dy->C + 31) / 32), 256, 0, st>>>((const bf16*)dy->ptr, dy->ld, dy->C, M, db);
-    rc = phs_check_launch("bias_grad_bf16");
-  }
-  return rc;
+  return db ? bias_grad_tc(dy, db, st) : 0;
 }

@@ -27,7 +27,18 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
 #pragma unroll
     for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
     if (lane_p < PL) {
-      for (int p = p0 + lane_p; p < p1; p += PL) {
+      constexpr int U = 4;   // independent 16-byte loads in flight per thread
+      int p = p0 + lane_p;
+      for (; p + (U - 1) * PL < p1; p += U * PL) {
+        float v[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) ldv<T, V>(base + (size_t)(p + u * PL) * ld + cv * V, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i) { s[i] += v[u][i]; q[i] += v[u][i] * v[u][i]; }
+      }
+      for (; p < p1; p += PL) {
         float v[V];
         ldv<T, V>(base + (size_t)p * ld + cv * V, v);
 #pragma unroll
@@ -75,7 +86,27 @@ __global__ void __launch_bounds__(RED_THREADS)
       be[i] = beta[c];
     }
     if (lane_p < PL) {
-      for (int p = p0 + lane_p; p < p1; p += PL) {
+      constexpr int U = 4;
+      int p = p0 + lane_p;
+      for (; p + (U - 1) * PL < p1; p += U * PL) {
+        float gv[U][V], yv[U][V];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ldv<T, V>(gb + (size_t)(p + u * PL) * ldg + cv * V, gv[u]);
+          ldv<T, V>(yb + (size_t)(p + u * PL) * ldy + cv * V, yv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float xh = (yv[u][i] - mu[i]) * rs[i];
+            float a = ga[i] * xh + be[i];
+            float gm = (relu && a <= 0.f) ? 0.f : gv[u][i];
+            s1[i] += gm;
+            s2[i] += gm * xh;
+          }
+      }
+      for (; p < p1; p += PL) {
         float gv[V], yv[V];
         ldv<T, V>(gb + (size_t)p * ldg + cv * V, gv);
         ldv<T, V>(yb + (size_t)p * ldy + cv * V, yv);
@@ -286,26 +317,73 @@ int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* me
 // ---------------------------------------------------------------------------------------------------------
 // streaming kernels: one thread per (pixel, channel-vector)
 // ---------------------------------------------------------------------------------------------------------
+// grid = (chunks, N); a block walks a contiguous run of pixels of ONE sample with CW channel-vector lanes x PL pixel
+// lanes; every thread keeps the normalisation parameters of its V channels in registers and has U independent
+// 16-byte loads in flight.
+constexpr int STREAM_U = 4;
+
+static void stream_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb) {
+  int nvec = C / V;
+  int CW = nvec < 256 ? nvec : 256;
+  int PL = 256 / CW;
+  int target_blocks = 148 * 8;
+  int chunks = (target_blocks + N - 1) / N;
+  int max_chunks = (HW + PL * STREAM_U - 1) / (PL * STREAM_U);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  *ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + *ppb - 1) / *ppb;
+  *grid = dim3(chunks, N);
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-    norm_act_fwd_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C, int64_t total,
+    norm_act_fwd_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C, int pix_per_block,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  const int n = blockIdx.y;
   const int nvec = C / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int n = (int)(pix / HW);
-    float v[V], o[V];
-    ldv<T, V>(y + pix * ldy + cv * V, v);
+  const int CW = nvec < 256 ? nvec : 256;
+  const int PL = 256 / CW;
+  const int lane_c = threadIdx.x % CW, lane_p = threadIdx.x / CW;
+  if (lane_p >= PL) return;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const T* yb = y + (size_t)n * HW * ldy;
+  T* ab = a + (size_t)n * HW * lda;
+  for (int cv = lane_c; cv < nvec; cv += CW) {
+    float sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       int c = cv * V + k;
-      float sc = gamma[c] * rstd[(size_t)n * C + c];
-      float r = (v[k] - mean[(size_t)n * C + c]) * sc + beta[c];
-      o[k] = (relu && r < 0.f) ? 0.f : r;
+      sc[k] = gamma[c] * rstd[(size_t)n * C + c];
+      sh[k] = beta[c] - mean[(size_t)n * C + c] * sc[k];
     }
-    stv<T, V>(a + pix * lda + cv * V, o);
+    int p = p0 + lane_p;
+    for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
+      float v[STREAM_U][V];
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) ldv<T, V>(yb + (size_t)(p + u * PL) * ldy + cv * V, v[u]);
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float r = fmaf(v[u][k], sc[k], sh[k]);
+          v[u][k] = (relu && r < 0.f) ? 0.f : r;
+        }
+        stv<T, V>(ab + (size_t)(p + u * PL) * lda + cv * V, v[u]);
+      }
+    }
+    for (; p < p1; p += PL) {
+      float v[V];
+      ldv<T, V>(yb + (size_t)p * ldy + cv * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float r = fmaf(v[k], sc[k], sh[k]);
+        v[k] = (relu && r < 0.f) ? 0.f : r;
+      }
+      stv<T, V>(ab + (size_t)p * lda + cv * V, v);
+    }
   }
 }
 
@@ -316,12 +394,11 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
               "phs_norm_act_fwd: y/a mismatch");
   int v = min_vec(pick_vec(y), pick_vec(a));
   int HW = y->H * y->W;
-  int64_t total = (int64_t)y->N * HW * (y->C / v);
-  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  if (blocks < 1) blocks = 1;
+  dim3 grid; int ppb;
+  stream_geometry(y->N, HW, y->C, v, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_kernel<T, V><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-                                                (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, total, mean, rstd,
+                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, ppb, mean, rstd,
                                                 gamma, beta, relu))));
   return phs_check_launch("norm_act_fwd");
 }
@@ -329,28 +406,68 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
     norm_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dy,
-                          int lddy, int HW, int C, int64_t total, const float* __restrict__ mean,
+                          int lddy, int HW, int C, int pix_per_block, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma,
                           const float* __restrict__ beta, int relu, const float* __restrict__ coef) {
+  const int n = blockIdx.y;
   const int nvec = C / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int n = (int)(pix / HW);
-    float gv[V], yv[V], o[V];
-    ldv<T, V>(g + pix * ldg + cv * V, gv);
-    ldv<T, V>(y + pix * ldy + cv * V, yv);
+  const int CW = nvec < 256 ? nvec : 256;
+  const int PL = 256 / CW;
+  const int lane_c = threadIdx.x % CW, lane_p = threadIdx.x / CW;
+  if (lane_p >= PL) return;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const T* gb = g + (size_t)n * HW * ldg;
+  const T* yb = y + (size_t)n * HW * ldy;
+  T* db = dy + (size_t)n * HW * lddy;
+  for (int cv = lane_c; cv < nvec; cv += CW) {
+    // a = sc*y + sh (activation input, for the ReLU mask);  xhat = rs*y + xo;  dy = gr*g' - k1 - xhat*k2
+    float sc[V], sh[V], rs[V], xo[V], gr[V], k1[V], k2[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       int c = cv * V + k;
       size_t nc = (size_t)n * C + c;
-      float rs = rstd[nc];
-      float xh = (yv[k] - mean[nc]) * rs;
-      float aa = gamma[c] * xh + beta[c];
-      float gm = (relu && aa <= 0.f) ? 0.f : gv[k];
-      o[k] = rs * (gm * gamma[c] - coef[nc * 2] - xh * coef[nc * 2 + 1]);
+      rs[k] = rstd[nc];
+      xo[k] = -mean[nc] * rs[k];
+      sc[k] = gamma[c] * rs[k];
+      sh[k] = beta[c] + gamma[c] * xo[k];
+      gr[k] = gamma[c] * rs[k];
+      k1[k] = rs[k] * coef[nc * 2];
+      k2[k] = rs[k] * coef[nc * 2 + 1];
     }
-    stv<T, V>(dy + pix * lddy + cv * V, o);
+    int p = p0 + lane_p;
+    for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
+      float gv[STREAM_U][V], yv[STREAM_U][V];
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) {
+        ldv<T, V>(gb + (size_t)(p + u * PL) * ldg + cv * V, gv[u]);
+        ldv<T, V>(yb + (size_t)(p + u * PL) * ldy + cv * V, yv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float xh = fmaf(yv[u][k], rs[k], xo[k]);
+          float aa = fmaf(yv[u][k], sc[k], sh[k]);
+          float gm = (relu && aa <= 0.f) ? 0.f : gv[u][k];
+          gv[u][k] = gm * gr[k] - k1[k] - xh * k2[k];
+        }
+        stv<T, V>(db + (size_t)(p + u * PL) * lddy + cv * V, gv[u]);
+      }
+    }
+    for (; p < p1; p += PL) {
+      float gv[V], yv[V];
+      ldv<T, V>(gb + (size_t)p * ldg + cv * V, gv);
+      ldv<T, V>(yb + (size_t)p * ldy + cv * V, yv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float xh = fmaf(yv[k], rs[k], xo[k]);
+        float aa = fmaf(yv[k], sc[k], sh[k]);
+        float gm = (relu && aa <= 0.f) ? 0.f : gv[k];
+        gv[k] = gm * gr[k] - k1[k] - xh * k2[k];
+      }
+      stv<T, V>(db + (size_t)p * lddy + cv * V, gv);
+    }
   }
 }
 
@@ -363,13 +480,12 @@ int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* me
               "phs_norm_bwd_apply: tensor mismatch");
   int v = min_vec(min_vec(pick_vec(y), pick_vec(g)), pick_vec(dy));
   int HW = y->H * y->W;
-  int64_t total = (int64_t)y->N * HW * (y->C / v);
-  int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  if (blocks < 1) blocks = 1;
+  dim3 grid; int ppb;
+  stream_geometry(y->N, HW, y->C, v, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_bwd_apply_kernel<T, V><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (norm_bwd_apply_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
-                                                HW, y->C, total, mean, rstd, gamma, beta, relu, coef))));
+                                                HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef))));
   return phs_check_launch("norm_bwd_apply");
 }
 

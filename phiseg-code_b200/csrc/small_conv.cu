@@ -1,0 +1,361 @@
+// Memory-bound convolutions with a tiny channel count on one side (tf.nn.conv2d SAME stride 1, tfwrapper/layers.py:123):
+//   - network inputs  (Cin in {1,2,3,5} -> 32..192 channels, 3x3): posterior/prior z0_pre_1, z*_ups_to_*_c_1, z*_post_1
+//   - heads           (32..192 channels -> Cout in {2,4,6}):        z*_mu, z*_sigma, y_lvl*, prediction, pre_mu/sigma
+// and the gradients of both.  These are dot products of a few hundred terms per pixel: no tensor cores, the job is to
+// stream the wide tensor once with 16-byte accesses.  fp32 master filters (HWIO), fp32 accumulation, any mix of
+// float32 / bfloat16 activations.
+#include "common.cuh"
+
+namespace {
+
+struct SmallGeom {
+  int N, H, W;
+  int Cin, Cout;  // channels of this launch's input / output tensors (roles swapped under dgrad)
+  int ks, dgrad;
+  int ldx, ldy;
+};
+
+// filter element seen by this launch: input channel a, output channel b, tap t (of THIS launch's correlation)
+__device__ __forceinline__ float wsel(const float* __restrict__ w, const SmallGeom& g, int t, int a, int b) {
+  const int taps = g.ks * g.ks;
+  if (!g.dgrad) return w[((size_t)t * g.Cin + a) * g.Cout + b];
+  return w[((size_t)(taps - 1 - t) * g.Cout + b) * g.Cin + a];   // dgrad: in = dy (co), out = dx (ci), taps flipped
+}
+
+// ---- wide input -> NOUT <= 8 outputs ----------------------------------------------------------------------------
+// TPP threads share a pixel (each takes every TPP-th 8-channel vector), partial dot products are combined by shuffles.
+// ksize 1: a thread's channels never change, so its filter slice lives in registers (MAXV vectors per thread);
+// ksize 3: compact [tap][Cin][NOUT] filter copy in shared memory.
+template <typename TI, typename TO, int TPP, int NOUT, int MAXV>
+__global__ void __launch_bounds__(256)
+    small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                      TO* __restrict__ y, SmallGeom g, int accumulate) {
+  extern __shared__ float ws[];  // ksize 3 only: [tap][Cin][NOUT]
+  const int taps = g.ks * g.ks;
+  const int nvec = g.Cin / 8;
+  const int sub = threadIdx.x % TPP;
+  constexpr int MV = MAXV > 0 ? MAXV : 1;
+  float wr[MV][8][NOUT];
+  if (MAXV > 0) {
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int cv = sub + j * TPP;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o)
+          wr[j][i][o] = (cv < nvec && o < g.Cout) ? wsel(w, g, 0, cv * 8 + i, o) : 0.f;
+    }
+  } else {
+    for (int i = threadIdx.x; i < taps * g.Cin * NOUT; i += blockDim.x) {
+      int o = i % NOUT, a = (i / NOUT) % g.Cin, t = (i / NOUT) / g.Cin;
+      ws[i] = o < g.Cout ? wsel(w, g, t, a, o) : 0.f;
+    }
+    __syncthreads();
+  }
+  const int64_t M = (int64_t)g.N * g.H * g.W;
+  const int pad = g.ks / 2;
+  // the loop bound is block-uniform: every lane takes part in the shuffles below
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < M * TPP; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix_raw = (base + threadIdx.x) / TPP;
+    const bool live = pix_raw < M;
+    const int64_t pix = live ? pix_raw : M - 1;
+    float acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
+    if (MAXV > 0) {
+      const TI* px = x + pix * g.ldx;
+      float v[MV][8];
+#pragma unroll
+      for (int j = 0; j < MAXV; ++j)
+        if (sub + j * TPP < nvec) ldv<TI, 8>(px + (sub + j * TPP) * 8, v[j]);
+#pragma unroll
+      for (int j = 0; j < MAXV; ++j)
+        if (sub + j * TPP < nvec) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(v[j][i], wr[j][i][o], acc[o]);
+        }
+    } else {
+      const int wq = (int)(pix % g.W);
+      const int hq = (int)((pix / g.W) % g.H);
+      for (int t = 0; t < taps; ++t) {
+        const int hh = hq + t / g.ks - pad, ww = wq + t % g.ks - pad;
+        if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
+        const TI* px = x + (pix + (int64_t)(hh - hq) * g.W + (ww - wq)) * g.ldx;
+        const float* wt = ws + (size_t)t * g.Cin * NOUT;
+        for (int cv = sub; cv < nvec; cv += TPP) {
+          float v[8];
+          ldv<TI, 8>(px + cv * 8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(v[i], wt[(cv * 8 + i) * NOUT + o], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = TPP / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (sub == 0 && live) {
+      TO* py = y + pix * g.ldy;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+        if (o < g.Cout) {
+          float r = acc[o] + (bias ? bias[o] : 0.f);
+          if (accumulate) r += ldf<TO>(py + o);
+          stf<TO>(py + o, r);
+        }
+    }
+  }
+}
+
+// ---- at most 8 input channels -> wide output --------------------------------------------------------------------
+// one thread per (pixel, 8-channel output vector)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+    small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     TO* __restrict__ y, SmallGeom g, int accumulate) {
+  extern __shared__ float ws[];  // [tap][Cin][Cout]
+  const int taps = g.ks * g.ks;
+  for (int i = threadIdx.x; i < taps * g.Cin * g.Cout; i += blockDim.x) {
+    int b = i % g.Cout, a = (i / g.Cout) % g.Cin, t = i / (g.Cout * g.Cin);
+    ws[i] = wsel(w, g, t, a, b);
+  }
+  __syncthreads();
+  const int nvec = g.Cout / 8;
+  const int64_t total = (int64_t)g.N * g.H * g.W * nvec;
+  const int pad = g.ks / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % nvec);
+    const int64_t pix = i / nvec;
+    const int wq = (int)(pix % g.W);
+    const int64_t t2 = pix / g.W;
+    const int hq = (int)(t2 % g.H);
+    float acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = bias ? bias[cv * 8 + o] : 0.f;
+    for (int t = 0; t < taps; ++t) {
+      const int hh = hq + t / g.ks - pad, ww = wq + t % g.ks - pad;
+      if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
+      const TI* px = x + (pix + (int64_t)(hh - hq) * g.W + (ww - wq)) * g.ldx;
+      for (int a = 0; a < g.Cin; ++a) {
+        const float xv = ldf<TI>(px + a);
+        const float* wt = ws + ((size_t)t * g.Cin + a) * g.Cout + cv * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wt);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+      }
+    }
+    TO* py = y + pix * g.ldy + cv * 8;
+    if (accumulate) {
+      float o[8];
+      ldv<TO, 8>(py, o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += o[k];
+    }
+    stv<TO, 8>(py, acc);
+  }
+}
+
+// ---- filter gradient with a tiny channel count on one side --------------------------------------------------------
+// dW[t][cs][cw] (small side = x, shifted by the tap)   or   dW[cw][cs] (ksize 1, small side = dy)
+//   = sum_p S[p + t][cs] * Wd[p][cw]
+// thread <-> (pair = (t, cs, 8-channel vector of the wide tensor), pixel lane); a block walks a contiguous pixel range
+// with PL lanes, 4 pixels in flight per thread; lanes are combined in shared memory, blocks with atomics.
+template <typename TS, typename TW>
+__global__ void __launch_bounds__(256)
+    wgrad_small_kernel(const TS* __restrict__ s, int lds, int Cs, const TW* __restrict__ wd, int ldw, int Cw, int N,
+                       int H, int W, int ks, int small_is_x, int64_t pix_per_block, int PB, float* __restrict__ dw) {
+  extern __shared__ float red[];  // [PB][8]
+  const int taps = ks * ks;
+  const int nvec = Cw / 8;
+  const int pairs = taps * Cs * nvec;
+  const int PL = blockDim.x / PB;
+  const int lp = threadIdx.x / PB;
+  const int pr = blockIdx.y * PB + threadIdx.x % PB;
+  for (int i = threadIdx.x; i < PB * 8; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const bool active = pr < pairs && lp < PL;
+  const int prc = pr < pairs ? pr : 0;
+  const int cv = prc % nvec, j = prc / nvec;
+  const int cs = j % Cs, t = j / Cs;
+  const int pad = ks / 2;
+  const int dh = t / ks - pad, dwv = t % ks - pad;
+  const int64_t M = (int64_t)N * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
+  float acc[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+  if (active) {
+    constexpr int U = 4;
+    // each pixel lane owns a contiguous sub-range: (h, w) are tracked incrementally, no divisions in the loop
+    const int64_t chunk = (pix_per_block + PL - 1) / PL;
+    int64_t p = p0 + (int64_t)lp * chunk;
+    const int64_t pe = p + chunk < p1 ? p + chunk : p1;
+    int wq = (int)(p % W);
+    int hq = (int)((p / W) % H);
+    for (; p < pe; p += U) {
+      float sv[U];
+      float v[U][8];
+      int ww = wq, hh = hq;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t q = p + u;
+        sv[u] = 0.f;
+        if (q < pe) {
+          const int h2 = hh + dh, w2 = ww + dwv;
+          if (h2 >= 0 && h2 < H && w2 >= 0 && w2 < W) sv[u] = ldf<TS>(s + (q + (int64_t)dh * W + dwv) * lds + cs);
+          ldv<TW, 8>(wd + q * ldw + cv * 8, v[u]);
+        } else {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) v[u][o] = 0.f;
+        }
+        if (++ww == W) {
+          ww = 0;
+          if (++hh == H) hh = 0;
+        }
+      }
+      wq = ww;
+      hq = hh;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(sv[u], v[u][o], acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) atomicAdd(&red[(threadIdx.x % PB) * 8 + o], acc[o]);
+  }
+  __syncthreads();
+  if (threadIdx.x < PB && pr < pairs) {
+    if (small_is_x) {
+      float* d = dw + ((size_t)t * Cs + cs) * Cw + cv * 8;   // [tap][ci = small][co = wide]
+#pragma unroll
+      for (int o = 0; o < 8; ++o) atomicAdd(d + o, red[threadIdx.x * 8 + o]);
+    } else {
+      float* d = dw + (size_t)(cv * 8) * Cs + cs;            // ksize 1: [ci = wide][co = small]
+#pragma unroll
+      for (int o = 0; o < 8; ++o) atomicAdd(d + (size_t)o * Cs, red[threadIdx.x * 8 + o]);
+    }
+  }
+}
+
+}  // namespace
+
+// returns 1 if handled, 0 if the shape is not for these kernels, <0 / >0 on error
+int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
+                   int accumulate, cudaStream_t st) {
+  SmallGeom g;
+  g.N = x->N; g.H = x->H; g.W = x->W; g.Cin = x->C; g.Cout = y->C; g.ks = ksize; g.dgrad = dgrad;
+  g.ldx = x->ld; g.ldy = y->ld;
+  const int taps = ksize * ksize;
+  const int64_t M = (int64_t)x->N * x->H * x->W;
+  const int xes = x->dtype == PHS_BF16 ? 2 : 4, yes = y->dtype == PHS_BF16 ? 2 : 4;
+  if (y->C <= 8 && x->C % 8 == 0 && x->C >= 8 && x->ld % 8 == 0 && ((uintptr_t)x->ptr % (8 * xes > 16 ? 16 : 8 * xes)) == 0) {
+    const int nout = y->C <= 2 ? 2 : y->C <= 4 ? 4 : 8;
+    const size_t smem = ksize == 1 ? 0 : (size_t)taps * x->C * nout * sizeof(float);
+    if (smem > 48 * 1024) return 0;
+    const int nvec = x->C / 8;
+    const int tpp = nvec >= 8 ? 8 : nvec >= 4 ? 4 : nvec >= 2 ? 2 : 1;
+    const int maxv = (nvec + tpp - 1) / tpp;
+    if (ksize == 1 && (maxv > 4 || (nout == 8 && maxv > 2))) return 0;
+    int64_t blocks = (M * tpp + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+#define LAUNCH_K(TI, TO, TPPV, NOUTV, MAXVV) \
+  small_cout_kernel<TI, TO, TPPV, NOUTV, MAXVV><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
+#define LAUNCH_V(TI, TO, TPPV, NOUTV)                          \
+  do {                                                         \
+    if (ksize != 1) LAUNCH_K(TI, TO, TPPV, NOUTV, 0);          \
+    else if (maxv == 1) LAUNCH_K(TI, TO, TPPV, NOUTV, 1);      \
+    else if (maxv == 2) LAUNCH_K(TI, TO, TPPV, NOUTV, 2);      \
+    else if (NOUTV < 8 && maxv == 3) LAUNCH_K(TI, TO, TPPV, (NOUTV < 8 ? NOUTV : 2), 3); \
+    else LAUNCH_K(TI, TO, TPPV, (NOUTV < 8 ? NOUTV : 2), 4);   \
+  } while (0)
+#define LAUNCH_N(TI, TO, TPPV)                    \
+  do {                                            \
+    if (nout == 2) LAUNCH_V(TI, TO, TPPV, 2);     \
+    else if (nout == 4) LAUNCH_V(TI, TO, TPPV, 4);\
+    else LAUNCH_V(TI, TO, TPPV, 8);               \
+  } while (0)
+#define LAUNCH_SC(TI, TO)                      \
+  do {                                         \
+    if (tpp == 8) LAUNCH_N(TI, TO, 8);         \
+    else if (tpp == 4) LAUNCH_N(TI, TO, 4);    \
+    else if (tpp == 2) LAUNCH_N(TI, TO, 2);    \
+    else LAUNCH_N(TI, TO, 1);                  \
+  } while (0)
+    if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_SC(float, float);
+    else if (x->dtype == PHS_F32) LAUNCH_SC(float, bf16);
+    else if (y->dtype == PHS_F32) LAUNCH_SC(bf16, float);
+    else LAUNCH_SC(bf16, bf16);
+#undef LAUNCH_SC
+#undef LAUNCH_N
+#undef LAUNCH_V
+#undef LAUNCH_K
+    int rc = phs_check_launch("small_cout_kernel");
+    return rc ? rc : 1;
+  }
+  if (x->C <= 8 && y->C % 8 == 0 && y->ld % 8 == 0 && ((uintptr_t)y->ptr % (8 * yes > 16 ? 16 : 8 * yes)) == 0) {
+    const size_t smem = (size_t)taps * x->C * y->C * sizeof(float);
+    if (smem > 48 * 1024) return 0;
+    int64_t total = M * (y->C / 8);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define LAUNCH_SI(TI, TO) \
+  small_cin_kernel<TI, TO><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
+    if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_SI(float, float);
+    else if (x->dtype == PHS_F32) LAUNCH_SI(float, bf16);
+    else if (y->dtype == PHS_F32) LAUNCH_SI(bf16, float);
+    else LAUNCH_SI(bf16, bf16);
+#undef LAUNCH_SI
+    int rc = phs_check_launch("small_cin_kernel");
+    return rc ? rc : 1;
+  }
+  return 0;
+}
+
+// dw must already hold the values to accumulate onto.  returns 1 if handled, 0 if not applicable.
+int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ksize, cudaStream_t st) {
+  const int64_t M = (int64_t)x->N * x->H * x->W;
+  const phs_tensor *s, *wd;
+  int small_is_x;
+  if (x->C <= 8 && dy->C % 8 == 0) {
+    s = x; wd = dy; small_is_x = 1;
+  } else if (dy->C <= 8 && x->C % 8 == 0 && ksize == 1) {
+    s = dy; wd = x; small_is_x = 0;
+  } else {
+    return 0;
+  }
+  const int wes = wd->dtype == PHS_BF16 ? 2 : 4;
+  if (wd->ld % 8 != 0 || ((uintptr_t)wd->ptr % (8 * wes > 16 ? 16 : 8 * wes)) != 0) return 0;
+  const int taps = ksize * ksize;
+  const int pairs = taps * s->C * (wd->C / 8);
+  // PB pairs per block (a multiple of 32, at most 256); the other 256 / PB thread groups are pixel lanes
+  int PB = pairs >= 256 ? 256 : ((pairs + 31) / 32) * 32;
+  if (PB == 96) PB = 128;
+  if (PB > 128 && PB < 256) PB = 256;
+  const int gy = (pairs + PB - 1) / PB;
+  int64_t splits = (148 * 4 + gy - 1) / gy;
+  if (splits > (M + 255) / 256) splits = (M + 255) / 256;
+  if (splits < 1) splits = 1;
+  const int64_t ppb = (M + splits - 1) / splits;
+  splits = (M + ppb - 1) / ppb;
+  dim3 grid((unsigned)splits, gy);
+  const size_t smem = (size_t)PB * 8 * sizeof(float);
+#define LAUNCH_WS(TS, TW)                                                                                             \
+  wgrad_small_kernel<TS, TW><<<grid, 256, smem, st>>>((const TS*)s->ptr, s->ld, s->C, (const TW*)wd->ptr, wd->ld, wd->C, \
+                                                      x->N, x->H, x->W, ksize, small_is_x, ppb, PB, dw)
+  if (s->dtype == PHS_F32 && wd->dtype == PHS_F32) LAUNCH_WS(float, float);
+  else if (s->dtype == PHS_F32) LAUNCH_WS(float, bf16);
+  else if (wd->dtype == PHS_F32) LAUNCH_WS(bf16, float);
+  else LAUNCH_WS(bf16, bf16);
+#undef LAUNCH_WS
+  int rc = phs_check_launch("wgrad_small_kernel");
+  return rc ? rc : 1;
+}

@@ -1,0 +1,242 @@
+// Filter gradient of a 3x3 SAME convolution on tcgen05, "halo" formulation (Conv2DBackpropFilter, the node
+// optimizer.minimize adds for tfwrapper/layers.py:123; phiseg_model.py:141).
+//
+//   dW[kh][kw][ci][co] = sum_{n,h,w} X[n, h+kh-1, w+kw-1, ci] * dY[n, h, w, co]
+//
+// The TMA unit is the scarce resource of the shifted-box kernel in conv_tc.cu (its cost is per 64/128-byte row, and
+// every tap re-loads the activation tile).  Here a CTA loads, per brick of 16 rows x 8 columns of one image, ONE halo
+// tile of X (16 x 10 pixels for its filter row kh) and one tile of dY, and feeds the three taps kw = 0,1,2 from the same
+// shared-memory tile through SHIFTED UMMA descriptors: both operands are MN-major (channels contiguous, one pixel per
+// 64/128-byte row), so a tap shift is a whole-row offset of the descriptor start address.  tools/umma_probe.cu shows
+// that tcgen05.mma applies the 64B/128B swizzle to absolute shared-memory address bits, so start addresses that are
+// not aligned to the swizzle pattern, and 8-row groups 10 rows apart (SBO = 10 rows), address the TMA-written tile
+// correctly with base_offset = 0.
+//
+//   M (128 rows of D)   = input channels.  Cin >= 128: a 128-channel block as two 64-channel halo boxes (LBO = box
+//                         stride), one accumulator per kw.  Cin = 64 / 32: the whole Cin for 2 / 4 CONSECUTIVE kw shifts
+//                         stacked along M, read from the same box with LBO = one pixel row (the 4th shift of a 3-wide
+//                         filter is computed and discarded).
+//   N                   = a block of output channels (<= 128 columns per accumulator, <= 3 accumulators in TMEM)
+//   K                   = pixels, 16 per MMA (two image rows of the brick), 8 MMAs per brick and accumulator
+//
+// A CTA owns (kh, ci block, co block, a slice of the bricks); partial sums go to the fp32 HWIO gradient with
+// red.global.add.v4.f32.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_host.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int WG_MAX_STAGES = 12;
+constexpr int HALO_W = 10;  // 8 + 2 columns
+constexpr int BR_H = 16, BR_W = 8;
+
+struct WgradHaloParams {
+  int N, H, W, Cin, Cout;
+  int bricksW, bricksH, num_bricks, bricks_per_split;
+  int slabw;       // channels per X box: 64 (128B swizzle) or 32 (64B swizzle)
+  int a_boxes;     // X boxes per stage (2 or 4 channel slabs, or 1 when kw shifts are stacked along M)
+  int a_lbo;       // bytes between the M slabs as the MMA sees them
+  int n_acc;       // accumulators = kw groups
+  int kw_step;     // kw distance between accumulators
+  int kw_per_acc;  // kw shifts stacked in one accumulator (1, 2 or 4)
+  int nb;          // output channels per CTA (N of the MMA)
+  int slabB, nslabB;
+  int ci_blocks, co_blocks;
+  int stages, tmem_cols;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rowA = p.slabw * 2, rowB = p.slabB * 2;
+  const uint32_t boxA_bytes = BR_H * HALO_W * rowA, boxB_bytes = BR_H * BR_W * rowB;
+  const uint32_t A_BYTES = boxA_bytes * p.a_boxes, B_BYTES = boxB_bytes * p.nslabB;
+  const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (WG_MAX_STAGES + s); };
+  const uint32_t tfull_bar = bar0 + 8u * (2 * WG_MAX_STAGES);
+
+  // work item: kh fastest so the three CTAs sharing the same bricks run together
+  int item = blockIdx.x;
+  const int kh = item % 3;
+  item /= 3;
+  const int cib = item % p.ci_blocks;
+  const int cob = item / p.ci_blocks;
+  const int t_begin = blockIdx.y * p.bricks_per_split;
+  const int t_end = min(p.num_bricks, t_begin + p.bricks_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int w0 = (t % p.bricksW) * BR_W;
+        const int h0 = ((t / p.bricksW) % p.bricksH) * BR_H;
+        const int n = t / (p.bricksW * p.bricksH);
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const uint32_t a_s = smem0 + s * STAGE_BYTES;
+        for (int j = 0; j < p.a_boxes; ++j)
+          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), cib * 128 + j * p.slabw, w0 - 1, h0 + kh - 1, n);
+        for (int j = 0; j < p.nslabB; ++j)
+          tma_load_4d(a_s + A_BYTES + j * boxB_bytes, &tmDY, full_bar(s), cob * p.nb + j * p.slabB, w0, h0, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, p.nb, 1, 1);
+      const uint64_t layA = p.slabw == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+      const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_s = smem0 + s * STAGE_BYTES;
+        const uint32_t b_s = a_s + A_BYTES;
+        for (int g = 0; g < p.n_acc; ++g) {
+          const uint32_t a_g = a_s + g * p.kw_step * rowA;   // tap shift = whole pixel rows of the halo tile
+#pragma unroll
+          for (int k = 0; k < BR_H / 2; ++k) {
+            // K step k = image rows 2k, 2k+1 of the brick: two groups of 8 pixels, HALO_W rows apart in the X tile,
+            // 8 rows apart in the dY tile
+            const uint64_t da = smem_desc(a_g + (2 * k) * HALO_W * rowA, p.a_lbo, HALO_W * rowA, layA);
+            const uint64_t db = smem_desc(b_s + (2 * k) * BR_W * rowB, boxB_bytes, BR_W * rowB, layB);
+            umma_bf16(tmem_base + g * p.nb, da, db, idesc, (it | k) != 0);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (t_begin < t_end) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    for (int g = 0; g < p.n_acc; ++g) {
+      int kw, ci;
+      if (p.kw_per_acc == 1) {
+        kw = g;
+        ci = cib * 128 + m;
+      } else {
+        kw = g * p.kw_step + m / p.slabw;
+        ci = m % p.slabw;
+      }
+      const bool valid = kw < 3 && ci < p.Cin;
+      float* dst = p.dw + ((size_t)((kh * 3 + (valid ? kw : 0)) * p.Cin + (valid ? ci : 0))) * p.Cout + cob * p.nb;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + g * p.nb;
+      for (int c0 = 0; c0 < p.nb; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t0 + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + i), "f"(__uint_as_float(r[i])),
+                         "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                         : "memory");
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize) {
+  return ksize == 3 && x->H % BR_H == 0 && x->W % BR_W == 0 && x->C % 32 == 0 && dy->C % 32 == 0 && dy->C <= 256;
+}
+
+// dw must already hold the values to accumulate onto (the caller zeroes it when accumulate == 0)
+int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st) {
+  WgradHaloParams p;
+  p.N = x->N; p.H = x->H; p.W = x->W; p.Cin = x->C; p.Cout = dy->C;
+  p.bricksW = x->W / BR_W;
+  p.bricksH = x->H / BR_H;
+  p.num_bricks = p.bricksW * p.bricksH * x->N;
+  if (x->C == 32 || x->C == 64) {
+    p.slabw = x->C;
+    p.a_boxes = 1;
+    p.a_lbo = x->C * 2;            // next M slab = the same tile one pixel further
+    p.kw_per_acc = 128 / x->C;
+    p.kw_step = p.kw_per_acc;
+    p.n_acc = (3 + p.kw_per_acc - 1) / p.kw_per_acc;
+    p.ci_blocks = 1;
+  } else {
+    p.slabw = x->C % 64 == 0 ? 64 : 32;
+    p.a_boxes = 128 / p.slabw;
+    p.a_lbo = BR_H * HALO_W * p.slabw * 2;
+    p.kw_per_acc = 1;
+    p.kw_step = 1;
+    p.n_acc = 3;
+    p.ci_blocks = (x->C + 127) / 128;
+  }
+  // output-channel block: n_acc * nb TMEM columns <= 512, nb <= 128 keeps the stage small
+  p.co_blocks = (dy->C + 127) / 128;
+  p.nb = dy->C / p.co_blocks;
+  if (p.nb % 32) {
+    p.co_blocks = dy->C / 32;
+    p.nb = 32;
+  }
+  p.slabB = p.nb % 64 == 0 ? 64 : 32;
+  p.nslabB = p.nb / p.slabB;
+  int cols = p.n_acc * p.nb;
+  p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  p.dw = dw;
+  const int stage_bytes = BR_H * HALO_W * p.slabw * 2 * p.a_boxes + BR_H * BR_W * p.nb * 2;
+  int stages = (SMEM_OPTIN - 2048) / stage_bytes;
+  if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  p.stages = stages;
+  const int items = 3 * p.ci_blocks * p.co_blocks;
+  int splits = (2 * num_sms() + items - 1) / items;
+  if (splits > p.num_bricks) splits = p.num_bricks;
+  if (splits < 1) splits = 1;
+  p.bricks_per_split = (p.num_bricks + splits - 1) / splits;
+  splits = (p.num_bricks + p.bricks_per_split - 1) / p.bricks_per_split;
+  CUtensorMap tmX, tmDY;
+  int rc = activation_map(x, p.slabw, HALO_W, BR_H, 1, &tmX);
+  if (rc) return rc;
+  rc = activation_map(dy, p.slabB, BR_W, BR_H, 1, &tmDY);
+  if (rc) return rc;
+  static bool attr = false;
+  if ((rc = allow_big_smem(wgrad_halo_kernel, &attr))) return rc;
+  const int smem = stages * stage_bytes + 2048;
+  wgrad_halo_kernel<<<dim3(items, splits), 192, smem, st>>>(tmX, tmDY, p);
+  return phs_check_launch("wgrad_halo_kernel");
+}
