@@ -1,0 +1,395 @@
+// 3x3 SAME convolution forward / input gradient on tcgen05, "halo" formulation (tf.nn.conv2d, tfwrapper/layers.py:123,
+// and Conv2DBackpropInput).  Same GEMM as conv_tc.cu,
+//
+//   D[pixel][cout] = sum_{tap, ci} X[pixel + tap][ci] * Wt[cout][tap*Cin + ci],
+//
+// but the activation operand is loaded ONCE per 64-channel chunk instead of once per tap: a CTA owns a super-tile of
+// 16 rows x 8*S columns of one image (S sub-tiles of 128 pixels, one TMEM accumulator each), loads the
+// 18 x (8*S+2) halo tile with one TMA box (out-of-bounds rows/columns zero-filled = SAME padding) and issues the MMAs of
+// all 9 taps and S sub-tiles from it through SHIFTED K-major descriptors: tap (kh,kw), sub-tile s start at halo pixel
+// (kh, 8*s + kw); the 8 pixels of one image row are contiguous 128-byte rows, the next image row is SBO = (8*S+2) rows
+// further.  tcgen05.mma applies the swizzle to absolute shared-memory address bits (tools/umma_probe.cu), so these
+// unaligned starts read the TMA-written tile correctly.  The TMA unit's cost is per 128-byte row: this cuts the
+// activation rows per MMA by ~6x and shares every filter tile between S sub-tiles.
+//
+//   warp 0: TMA producer (A ring: halo tiles; B ring: one [Cout][64] filter tile per (chunk, tap); when the whole
+//           filter fits it is loaded once and stays resident)
+//   warp 1: MMA issuer, accumulators double-buffered in TMEM (2 x S x Cout <= 512 columns)
+//   warps 2-5: epilogue: tcgen05.ld -> +bias -> bf16/f32 store, and the per-(sample, channel) sum / sum of squares the
+//           following batch_norm / group_norm2D needs (tfwrapper/normalisation.py:27-34,156) from the fp32 accumulators:
+//           32-lane butterfly transpose-reduce per 16 columns, accumulated in registers while the CTA stays inside one
+//           image (CTAs own contiguous tile ranges), then one red.global.add per (channel, quantity).
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_host.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int HB_MAX_A = 3, HB_MAX_B = 40;
+constexpr int TILE_H = 16, SUB_W = 8;
+
+struct HaloParams {
+  int N, H, W, Cin, Cout;
+  int S;                      // sub-tiles per super-tile
+  int tilesW, tilesH, num_tiles;
+  int kchunks;
+  int na, nb, b_resident;
+  int acc_stages, acc_cols, tmem_cols;   // TMEM: acc_stages accumulator sets of acc_cols columns
+  uint32_t a_stage_bytes;     // rounded up to 1024
+  void* y;
+  int y_ld, y_f32;
+  const float* bias;
+  int accumulate;
+  float* stats;               // [N][Cout][2] or null
+  int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
+};
+
+template <typename T>
+__device__ __forceinline__ void store16(T* dst, const float* v, bool accumulate) {
+  float o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i] = v[i];
+  if (accumulate) {
+    float p[16];
+    ldv<T, 8>(dst, p);
+    ldv<T, 8>(dst + 8, p + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] += p[i];
+  }
+  stv<T, 8>(dst, o);
+  stv<T, 8>(dst + 8, o + 8);
+}
+
+// sum over the 32 lanes of each of 16 per-lane values; lane L ends up with the total of column col16(L)
+__device__ __forceinline__ int col16(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+__device__ __forceinline__ float transpose_reduce16(const float* v, int lane) {
+  float a8[8], a4[4], a2[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float send = up ? v[i] : v[i + 8];
+    float keep = up ? v[i + 8] : v[i];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = up ? a8[i] : a8[i + 4];
+    float keep = up ? a8[i + 4] : a8[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = up ? a4[i] : a4[i + 2];
+    float keep = up ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+  float send = up ? a2[0] : a2[1];
+  float keep = up ? a2[1] : a2[0];
+  float a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
+
+template <int BK>
+__global__ void __launch_bounds__(192, 2)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * HB_MAX_A + 2 * HB_MAX_B + 4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t ROW = BK * 2;
+  const int HW_ = SUB_W * p.S + 2;                 // halo width in pixels
+  const uint32_t a_bytes = (uint32_t)(TILE_H + 2) * HW_ * ROW;
+  const uint32_t b_bytes = (uint32_t)p.Cout * ROW;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_b0 = smem0 + p.na * p.a_stage_bytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto a_full = [&](int s) { return bar0 + 8u * s; };
+  auto a_empty = [&](int s) { return bar0 + 8u * (HB_MAX_A + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * HB_MAX_A + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (2 * HB_MAX_A + HB_MAX_B + s); };
+  auto tfull = [&](int a) { return bar0 + 8u * (2 * HB_MAX_A + 2 * HB_MAX_B + a); };
+  auto tempty = [&](int a) { return bar0 + 8u * (2 * HB_MAX_A + 2 * HB_MAX_B + 2 + a); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.na; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < p.nb; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull(a), 1);
+      mbar_init(tempty(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // contiguous tile range of this CTA
+  const int t_begin = (int)((int64_t)p.num_tiles * blockIdx.x / gridDim.x);
+  const int t_end = (int)((int64_t)p.num_tiles * (blockIdx.x + 1) / gridDim.x);
+  const int tiles_per_img = p.tilesW * p.tilesH;
+
+  // The two issue loops below run on one warp each and every instruction in them is on the critical path of the
+  // tensor pipe (the UTCHMMA instructions themselves never stall): ring indices and phase bits are counters (no
+  // runtime division), the tap loop is unrolled so tap offsets are immediates, kernel parameters sit in registers.
+  const int S = p.S, kchunks = p.kchunks, na = p.na, nb = p.nb, resident = p.b_resident, Cout = p.Cout, Cin = p.Cin;
+  const int tilesW = p.tilesW, acc_stages = p.acc_stages, dbg = p.dbg;
+  const uint32_t a_stage_bytes = p.a_stage_bytes, acc_cols = p.acc_cols;
+  if (warp == 0) {
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    int n = t_begin / tiles_per_img;
+    int r = t_begin - n * tiles_per_img;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int th = r / tilesW;
+      const int h0 = th * TILE_H, w0 = (r - th * tilesW) * SUB_W * S;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(a_empty(sa), pha ^ 1);
+        if (elect_one()) {
+          if (dbg & 1) {
+            mbar_arrive(a_full(sa));
+          } else {
+            mbar_expect_tx(a_full(sa), a_bytes);
+            tma_load_4d(smem0 + sa * a_stage_bytes, &tmA, a_full(sa), kc * BK, w0 - 1, h0 - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++sa == na) { sa = 0; pha ^= 1; }
+        if (resident && tile != t_begin) continue;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int sbi = resident ? kc * 9 + tap : sb;
+          if (!resident) mbar_wait(b_empty(sbi), phb ^ 1);
+          if (elect_one()) {
+            if (dbg & 1) {
+              mbar_arrive(b_full(sbi));
+            } else {
+              mbar_expect_tx(b_full(sbi), b_bytes);
+              tma_load_2d(smem_b0 + sbi * b_bytes, &tmB, b_full(sbi), tap * Cin + kc * BK, 0);
+            }
+          }
+          __syncwarp();
+          if (!resident && ++sb == nb) { sb = 0; phb ^= 1; }
+        }
+      }
+      if (++r == tiles_per_img) { r = 0; ++n; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_bf16(128, Cout, 0, 0);
+    constexpr uint64_t LAYOUT = BK == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t a_hi = desc_hi(HW_ * ROW, LAYOUT);   // SBO: next image row of the sub-tile inside the halo tile
+    const uint32_t b_hi = desc_hi(8 * ROW, LAYOUT);
+    const uint32_t hw16 = (HW_ * ROW) >> 4;             // one halo row, in descriptor (16-byte) units
+    const uint32_t b_base_lo = desc_lo(smem_b0, 16), b_step = b_bytes >> 4;
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pha = 0, phb = 0, aph = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(tempty(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * acc_cols;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(a_full(sa), pha);
+        tc_fence_after();
+        const uint32_t a_base_lo = desc_lo(smem0 + sa * a_stage_bytes, 16);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int sbi = resident ? kc * 9 + tap : sb;
+          mbar_wait(b_full(sbi), resident ? 0u : phb);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t b_lo = b_base_lo + sbi * b_step;
+            uint32_t a_lo = a_base_lo + (tap / 3) * hw16 + (tap % 3) * (ROW >> 4);
+            uint32_t d = d0;
+            const uint32_t first = tap != 0 ? 1u : (kc != 0 ? 1u : 0u);
+            for (int sub = 0; sub < S; ++sub, a_lo += (SUB_W * ROW) >> 4, d += Cout) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                if (!(dbg & 2)) umma_bf16_lohi(d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, k ? 1u : first);
+            }
+            if (!resident) umma_commit(b_empty(sbi));
+            if (tap == 8) {
+              umma_commit(a_empty(sa));
+              if (kc == kchunks - 1) umma_commit(tfull(acc));
+            }
+          }
+          __syncwarp();
+          if (!resident && ++sb == nb) { sb = 0; phb ^= 1; }
+        }
+        if (++sa == na) { sa = 0; pha ^= 1; }
+      }
+      if (++acc == acc_stages) { acc = 0; aph ^= 1; }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t tcount = 0;
+    // running per-channel statistics of the current image: chunk j holds column 16*j + col16(lane)
+    float st_s[16], st_q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) st_s[j] = st_q[j] = 0.f;
+    int st_n = -1;
+    auto flush = [&]() {
+      if (p.stats && st_n >= 0) {
+        float* dst = p.stats + (size_t)st_n * p.Cout * 2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j * 16 < p.Cout) {
+            const int c = j * 16 + col16(lane);
+            atomicAdd(dst + c * 2 + (lane & 1), (lane & 1) ? st_q[j] : st_s[j]);
+            st_s[j] = st_q[j] = 0.f;
+          }
+      }
+    };
+    for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
+      const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
+      const int n = tile / tiles_per_img;
+      const int r = tile - n * tiles_per_img;
+      const int h = (r / p.tilesW) * TILE_H + m / SUB_W;
+      const int wbase = (r % p.tilesW) * SUB_W * p.S + m % SUB_W;
+      if (n != st_n) {
+        flush();
+        st_n = n;
+      }
+      mbar_wait(tfull(acc), aph);
+      tc_fence_after();
+      for (int s = 0; s < p.S; ++s) {
+        const size_t pix = ((size_t)n * p.H + h) * p.W + wbase + s * SUB_W;
+        const uint32_t t0 = tmem_base + acc * p.acc_cols + s * p.Cout + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j * 16 < p.Cout) {
+            uint32_t rr[16];
+            tmem_ld16(t0 + j * 16, rr);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[j * 16 + i];
+            if (p.dbg & 4) {
+            } else if (p.y_f32) store16<float>((float*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
+            else store16<bf16>((bf16*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
+            if (p.stats) {
+              float sq[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+              st_s[j] += transpose_reduce16(v, lane);
+              st_q[j] += transpose_reduce16(sq, lane);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+    }
+    flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+}  // namespace
+
+bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
+  return ksize == 3 && x->H % TILE_H == 0 && x->W % SUB_W == 0 && x->C % 32 == 0 && y->C % 16 == 0 && y->C >= 16 &&
+         y->C <= 256;
+}
+
+int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate,
+                float* stats, cudaStream_t st) {
+  const int BK = x->C % 64 == 0 ? 64 : 32;
+  const int ROW = BK * 2;
+  HaloParams p;
+  p.N = x->N; p.H = x->H; p.W = x->W; p.Cin = x->C; p.Cout = y->C;
+  p.kchunks = x->C / BK;
+  const int subs_w = x->W / SUB_W;
+  const int64_t total_subs = (int64_t)x->N * (x->H / TILE_H) * subs_w;
+  // Two CTAs per SM (each <= 256 TMEM columns, ~110 KB of shared memory): while one CTA drains its accumulators or
+  // waits on a barrier, the other one keeps the tensor pipe busy.  One accumulator set of S sub-tiles per CTA.
+  // S: as many sub-tiles as TMEM, the halo stage budget and the image width allow, leaving >= 2 super-tiles per SM.
+  const int budget = getenv("PHS_HALO_1CTA") ? SMEM_OPTIN - 2048 : 110 * 1024;
+  const int max_cols = 256;
+  int S = 1;
+  while (S * 2 * y->C <= max_cols && subs_w % (S * 2) == 0 &&
+         2 * ((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024 + 4 * y->C * ROW <= budget &&
+         total_subs / (S * 2) >= 2 * num_sms())
+    S *= 2;
+  p.S = S;
+  p.tilesW = subs_w / S;
+  p.tilesH = x->H / TILE_H;
+  p.num_tiles = p.tilesW * p.tilesH * x->N;
+  const int a_bytes = (TILE_H + 2) * (SUB_W * S + 2) * ROW;
+  p.a_stage_bytes = (a_bytes + 1023) / 1024 * 1024;
+  const int b_bytes = y->C * ROW;
+  const int cols = S * y->C;
+  p.acc_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
+  // double-buffer the accumulators whenever the CTA's TMEM share allows it (the epilogue of tile i then overlaps the
+  // MMAs of tile i+1 inside the CTA as well)
+  const int tmem_share = getenv("PHS_HALO_1CTA") ? 512 : 256;
+  p.acc_stages = 2 * p.acc_cols <= tmem_share ? 2 : 1;
+  p.tmem_cols = p.acc_cols * p.acc_stages;
+  // filter resident?
+  const int b_all = p.kchunks * 9 * b_bytes;
+  if (p.kchunks * 9 <= HB_MAX_B && b_all + 2 * (int)p.a_stage_bytes <= budget) {
+    p.b_resident = 1;
+    p.nb = p.kchunks * 9;
+    p.na = (budget - b_all) / (int)p.a_stage_bytes;
+    if (p.na > HB_MAX_A) p.na = HB_MAX_A;
+  } else {
+    p.b_resident = 0;
+    p.na = 2;
+    p.nb = (budget - 2 * (int)p.a_stage_bytes) / b_bytes;
+    if (p.nb > 12) p.nb = 12;
+    if (p.nb < 2) return -3;   // caller falls back to the shifted-box kernel
+  }
+  p.y = y->ptr; p.y_ld = y->ld; p.y_f32 = y->dtype == PHS_F32;
+  p.bias = bias;
+  p.accumulate = accumulate;
+  p.stats = stats;
+  {
+    const char* e = getenv("PHS_HALO_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = activation_map(x, BK, SUB_W * S + 2, TILE_H + 2, 1, &tmA);
+  if (rc) return rc;
+  rc = filter_map(w, 9 * x->C, y->C, BK, &tmB);
+  if (rc) return rc;
+  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + 1024;
+  const int ctas = (getenv("PHS_HALO_1CTA") ? 1 : 2) * num_sms();
+  const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
+  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
+  if (BK == 64) {
+    static bool attr = false;
+    if ((rc = allow_big_smem(conv_halo_kernel<64>, &attr))) return rc;
+    conv_halo_kernel<64><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  } else {
+    static bool attr = false;
+    if ((rc = allow_big_smem(conv_halo_kernel<32>, &attr))) return rc;
+    conv_halo_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, p);
+  }
+  return phs_check_launch("conv_halo_kernel");
+}

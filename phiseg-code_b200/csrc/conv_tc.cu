@@ -475,10 +475,15 @@ __global__ void __launch_bounds__(256) bias_grad_bf16_kernel(const bf16* __restr
 // ------------------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------------------
+bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize);
+int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate, float* stats,
+                cudaStream_t st);
+bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
+int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
+
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
               int accumulate, float* stats, cudaStream_t st) {
   // the gradient w.r.t. the input is the same GEMM on the dgrad filter shadow
-  PHS_REQUIRE(stats == nullptr, "conv2d_tc: fused statistics are not available in this build");
   PHS_REQUIRE(x->dtype == PHS_BF16, "conv2d_tc: input must be bf16");
   PHS_REQUIRE(x->C % 32 == 0 && y->C % 16 == 0 && y->C >= 16,
               "conv2d_tc: Cin=%d must be a multiple of 32 and Cout=%d a multiple of 16", x->C, y->C);
@@ -493,6 +498,7 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
       ys.ptr = (char*)y->ptr + (size_t)c0 * es;
       ys.C = y->C - c0 < part ? y->C - c0 : part;
       const bf16* ws = (const bf16*)w + (size_t)c0 * ksize * ksize * x->C;
+      PHS_REQUIRE(stats == nullptr, "conv2d_tc: fused statistics need Cout <= 256");
       int rc = conv2d_tc(x, ws, bias ? bias + c0 : nullptr, &ys, ksize, dgrad, accumulate, nullptr, st);
       if (rc) return rc;
     }
@@ -501,6 +507,16 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   PHS_REQUIRE(x->ld % 8 == 0 && aligned16(x->ptr) && aligned16(w), "conv2d_tc: input / filter not 16-byte aligned");
   const int yes = y->dtype == PHS_F32 ? 4 : 2;
   PHS_REQUIRE(((size_t)y->ld * yes) % 16 == 0 && aligned16(y->ptr), "conv2d_tc: output not 16-byte aligned");
+  if (conv_halo_eligible(x, y, ksize) && !getenv("PHS_NO_HALO")) {
+    int rc = conv2d_halo(x, w, bias, y, accumulate, stats, st);
+    if (rc != -3) return rc;
+  }
+  if (stats) {
+    // shapes the halo kernel does not take: plain convolution, then a separate statistics pass over y
+    int rc = conv2d_tc(x, w, bias, y, ksize, dgrad, accumulate, nullptr, st);
+    if (rc) return rc;
+    return phs_chan_stats(y, stats, st);
+  }
   const int BK = x->C % 64 == 0 ? 64 : 32;
   const int taps = ksize * ksize;
   Brick b = make_brick(x->N, x->H, x->W, 128);
@@ -534,9 +550,6 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   }
   return phs_check_launch("conv_tc_kernel");
 }
-
-bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
-int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
 
 static int bias_grad_tc(const phs_tensor* dy, float* db, cudaStream_t st) {
   const int64_t M = (int64_t)dy->N * dy->H * dy->W;

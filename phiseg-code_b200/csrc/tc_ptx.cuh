@@ -8,6 +8,22 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (the same lane every time): all role loops run warp-uniform and only the issue of
+// TMA / tcgen05 instructions is predicated on this, which lets ptxas use the uniform datapath without election loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -79,6 +95,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same, with the descriptors passed as (lo, hi) halves.  The uniform datapath that feeds UTCHMMA is a scalar unit with
+// ~10-cycle dependent latency: building a descriptor from scratch (shift, mask, or, or, pack) in front of every MMA costs
+// 60-80 cycles per instruction, more than a narrow MMA takes.  Callers keep `hi` constant and advance `lo` (start
+// address >> 4, bits 0-13; LBO >> 4 in bits 16-29) with one add per MMA.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint64_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)layout << 29);
 }
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

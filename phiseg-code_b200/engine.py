@@ -415,9 +415,15 @@ class Builder:
             nb = None
         else:
             y = self.new(x.N, x.H, x.W, cout, ydt)
-            self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
             mode, eps = self._norm_mode()
             N, HW, C = x.N, x.H * x.W, cout
+            stats = pr.vec(N * C * 2)
+            fused_stats = tc and mode != L.NORM_BN_INFER
+            if fused_stats:
+                # statistics of the following norm come out of the conv epilogue (fp32 accumulators)
+                self.emit('phs_conv2d_stats', x.desc(), w_f, bias, y.desc(), k, stats.data_ptr())
+            else:
+                self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
             if cfg.norm == 'batch_norm':
                 pre = scope + '/batch_norm/BatchNorm/'
                 gamma, beta = P.ptr(pre + 'gamma'), P.ptr(pre + 'beta')
@@ -428,9 +434,8 @@ class Builder:
                 gamma, beta = P.ptr(pre + 'gamma'), P.ptr(pre + 'beta')
                 dgamma, dbeta = P.ptr(pre + 'gamma', 'g'), P.ptr(pre + 'beta', 'g')
                 mm = mv = None
-            stats = pr.vec(N * C * 2)
             mean, rstd = pr.vec(N * C), pr.vec(N * C)
-            if mode != L.NORM_BN_INFER:
+            if mode != L.NORM_BN_INFER and not fused_stats:
                 self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
             self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
                       rstd.data_ptr())

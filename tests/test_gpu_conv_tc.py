@@ -136,3 +136,26 @@ def test_conv_tc_large_linearity(call, lib):
     # one image against cuDNN-free torch on the GPU (exact integer arithmetic again)
     ref = torch.nn.functional.conv2d(x1[:1].float().permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=1)
     assert torch.equal(ref.permute(0, 2, 3, 1), outs[0][:1])
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(3, 16, 16, 64, 64), (2, 32, 32, 128, 128), (2, 128, 128, 32, 32),
+                                            (2, 64, 64, 192, 64), (3, 8, 8, 192, 192), (2, 16, 32, 256, 192)])
+def test_conv_tc_fused_statistics(call, lib, oracle, N, H, W, Cin, Cout):
+    """phs_conv2d_stats: convolution + the per-(sample, channel) sum / sum of squares batch_norm / group_norm2D need
+    (tfwrapper/normalisation.py:27-34,156), taken from the fp32 accumulators in the epilogue (halo kernel) or by a
+    separate pass (other shapes)."""
+    g = torch.Generator().manual_seed(N + H + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3, 3, Cin, Cout, generator=g) * (1.0 / np.sqrt(9 * Cin))).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g)
+    y = oracle.conv2d_same(x.double(), w.double(), b.double())
+    wf, _ = shadows(w.float())
+    yb = torch.zeros(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    stats = torch.full((N, Cout, 2), 5.0, device='cuda')
+    call('phs_conv2d_stats', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, stats)
+    assert relerr(yb, y) < 2 ** -8
+    s_ref = y.sum(dim=(1, 2))
+    q_ref = (y * y).sum(dim=(1, 2))
+    # the separate pass sees the bf16-rounded y, the fused epilogue the fp32 accumulators
+    assert relerr(stats[..., 0], s_ref) < 5e-3
+    assert relerr(stats[..., 1], q_ref) < 5e-3
