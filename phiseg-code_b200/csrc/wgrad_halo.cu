@@ -92,52 +92,64 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  // lean, warp-uniform issue loops (see conv_halo.cu): counters instead of divisions, descriptors advanced by adds
+  const int stages = p.stages, a_boxes = p.a_boxes, nslabB = p.nslabB, n_acc = p.n_acc, nb = p.nb;
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int w0 = (t % p.bricksW) * BR_W;
-        const int h0 = ((t / p.bricksW) % p.bricksH) * BR_H;
-        const int n = t / (p.bricksW * p.bricksH);
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    const int bpi = p.bricksW * p.bricksH;
+    int n = t_begin / bpi;
+    int r = t_begin - n * bpi;
+    const int c_a = cib * 128, c_b = cob * nb;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int bh = r / p.bricksW;
+      const int w0 = (r - bh * p.bricksW) * BR_W, h0 = bh * BR_H;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), STAGE_BYTES);
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
-        for (int j = 0; j < p.a_boxes; ++j)
-          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), cib * 128 + j * p.slabw, w0 - 1, h0 + kh - 1, n);
-        for (int j = 0; j < p.nslabB; ++j)
-          tma_load_4d(a_s + A_BYTES + j * boxB_bytes, &tmDY, full_bar(s), cob * p.nb + j * p.slabB, w0, h0, n);
+        for (int j = 0; j < a_boxes; ++j)
+          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), c_a + j * p.slabw, w0 - 1, h0 + kh - 1, n);
+        for (int j = 0; j < nslabB; ++j)
+          tma_load_4d(a_s + A_BYTES + j * boxB_bytes, &tmDY, full_bar(s), c_b + j * p.slabB, w0, h0, n);
       }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1; }
+      if (++r == bpi) { r = 0; ++n; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(128, p.nb, 1, 1);
-      const uint64_t layA = p.slabw == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      uint32_t it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    const uint32_t idesc = idesc_bf16(128, nb, 1, 1);
+    const uint64_t layA = p.slabw == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    // MN-major: LBO = distance between channel slabs (or one pixel row when kw shifts are stacked along M),
+    // SBO = distance between groups of 8 pixels (HALO_W rows in the X tile, 8 rows in the dY tile)
+    const uint32_t a_hi = desc_hi(HALO_W * rowA, layA), b_hi = desc_hi(BR_W * rowB, layB);
+    const uint32_t a_kstep = (2 * HALO_W * rowA) >> 4, b_kstep = (2 * BR_W * rowB) >> 4;
+    const uint32_t a_gstep = (p.kw_step * rowA) >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t first = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
-        const uint32_t b_s = a_s + A_BYTES;
-        for (int g = 0; g < p.n_acc; ++g) {
-          const uint32_t a_g = a_s + g * p.kw_step * rowA;   // tap shift = whole pixel rows of the halo tile
+        uint32_t a_lo = desc_lo(a_s, p.a_lbo);
+        const uint32_t b_lo = desc_lo(a_s + A_BYTES, boxB_bytes);
+        uint32_t d = tmem_base;
+        for (int g = 0; g < n_acc; ++g, a_lo += a_gstep, d += nb) {
 #pragma unroll
-          for (int k = 0; k < BR_H / 2; ++k) {
-            // K step k = image rows 2k, 2k+1 of the brick: two groups of 8 pixels, HALO_W rows apart in the X tile,
-            // 8 rows apart in the dY tile
-            const uint64_t da = smem_desc(a_g + (2 * k) * HALO_W * rowA, p.a_lbo, HALO_W * rowA, layA);
-            const uint64_t db = smem_desc(b_s + (2 * k) * BR_W * rowB, boxB_bytes, BR_W * rowB, layB);
-            umma_bf16(tmem_base + g * p.nb, da, db, idesc, (it | k) != 0);
-          }
+          for (int k = 0; k < BR_H / 2; ++k)
+            umma_bf16_lohi(d, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, k ? 1u : first);
         }
         umma_commit(empty_bar(s));
+        if (t == t_end - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      first = 1;
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
+    if (t_begin >= t_end && elect_one()) umma_commit(tfull_bar);
   } else if (t_begin < t_end) {
     const int q = warp & 3;
     const int m = q * 32 + lane;
