@@ -234,56 +234,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_s;
   const int kiters = p.taps * p.kchunks;
 
+  // lean, warp-uniform issue loops: ring index / phase are counters, descriptors advance by adds (see conv_halo.cu)
+  const int stages = p.stages, kchunks = p.kchunks, taps = p.taps, Cin = p.Cin;
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int w0 = (tile % p.tilesW) * p.TW;
-        const int h0 = ((tile / p.tilesW) % p.tilesH) * p.TH;
-        const int n0 = (tile / (p.tilesW * p.tilesH)) * p.TN;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dh = p.taps == 9 ? tap / 3 - 1 : 0;
-          const int dw = p.taps == 9 ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            mbar_wait(empty_bar(s), ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int w0 = (tile % p.tilesW) * p.TW;
+      const int h0 = ((tile / p.tilesW) % p.tilesH) * p.TH;
+      const int n0 = (tile / (p.tilesW * p.tilesH)) * p.TN;
+      int dh = taps == 9 ? -1 : 0, dw = dh;
+#pragma unroll 1
+      for (int tap = 0; tap < taps; ++tap) {
+#pragma unroll 1
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(full_bar(s), STAGE_BYTES);
             const uint32_t a_s = smem0 + s * STAGE_BYTES;
             tma_load_4d(a_s, &tmA, full_bar(s), kc * BK, w0 + dw, h0 + dh, n0);
-            tma_load_2d(a_s + A_BYTES, &tmB, full_bar(s), tap * p.Cin + kc * BK, 0);
+            tma_load_2d(a_s + A_BYTES, &tmB, full_bar(s), tap * Cin + kc * BK, 0);
           }
+          __syncwarp();
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
+        if (++dw == 2) { dw = -1; ++dh; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
-      constexpr uint64_t LAYOUT = BK == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      constexpr uint32_t SBO = BK == 64 ? 1024 : 512;
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
+    const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
+    constexpr uint64_t LAYOUT = BK == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    constexpr uint32_t SBO = BK == 64 ? 1024 : 512;
+    const uint32_t hi = desc_hi(SBO, LAYOUT);
+    const uint32_t a0_lo = desc_lo(smem0, 16), b0_lo = desc_lo(smem0 + A_BYTES, 16), stage16 = STAGE_BYTES >> 4;
+    int s = 0;
+    uint32_t ph = 0, acc = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 256;
+#pragma unroll 1
+      for (int kit = 0; kit < kiters; ++kit) {
+        mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * 256;
-        for (int kit = 0; kit < kiters; ++kit, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t a_s = smem0 + s * STAGE_BYTES;
-          const uint32_t b_s = a_s + A_BYTES;
+        if (elect_one()) {
+          const uint32_t a_lo = a0_lo + s * stage16, b_lo = b0_lo + s * stage16;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = smem_desc(a_s + k * 32, 16, SBO, LAYOUT);
-            const uint64_t db = smem_desc(b_s + k * 32, 16, SBO, LAYOUT);
-            umma_bf16(d, da, db, idesc, (kit | k) != 0);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_lohi(d, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, k ? 1u : (kit != 0 ? 1u : 0u));
           umma_commit(empty_bar(s));
+          if (kit == kiters - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++s == stages) { s = 0; ph ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) aph ^= 1;
     }
   } else {
     const int q = warp & 3;  // TMEM lane quadrant this warp may read
@@ -378,18 +384,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
+  const int stages = p.stages;
   if (warp == 0) {
-    if (lane == 0) {
-      const int dh = p.taps == 9 ? tap / 3 - 1 : 0;
-      const int dw = p.taps == 9 ? tap % 3 - 1 : 0;
-      uint32_t it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const int w0 = (tile % p.tilesW) * p.TW;
-        const int h0 = ((tile / p.tilesW) % p.tilesH) * p.TH;
-        const int n0 = (tile / (p.tilesW * p.tilesH)) * p.TN;
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+    const int dh = p.taps == 9 ? tap / 3 - 1 : 0;
+    const int dw = p.taps == 9 ? tap % 3 - 1 : 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int w0 = (tile % p.tilesW) * p.TW;
+      const int h0 = ((tile / p.tilesW) % p.tilesH) * p.TH;
+      const int n0 = (tile / (p.tilesW * p.tilesH)) * p.TN;
+      mbar_wait(empty_bar(s), ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), STAGE_BYTES);
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
         for (int j = 0; j < p.nslabA; ++j)
@@ -397,31 +403,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int j = 0; j < p.nslabB; ++j)
           tma_load_4d(a_s + A_BYTES + j * slabB_bytes, &tmDY, full_bar(s), j * p.slabB, w0, h0, n0);
       }
+      __syncwarp();
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = idesc_bf16(128, p.Cout, 1, 1);
-      const uint64_t layA = p.slabA == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
-      const uint32_t rowA = p.slabA * 2, rowB = p.slabB * 2;  // bytes per pixel row inside a slab
-      uint32_t it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
+    const uint32_t idesc = idesc_bf16(128, p.Cout, 1, 1);
+    const uint64_t layA = p.slabA == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
+    const uint32_t rowA = p.slabA * 2, rowB = p.slabB * 2;  // bytes per pixel row inside a slab
+    // MN-major: LBO = distance between 64(32)-channel slabs, SBO = distance between groups of 8 pixels
+    const uint32_t a_hi = desc_hi(8 * rowA, layA), b_hi = desc_hi(8 * rowB, layB);
+    const uint32_t a_k = (16 * rowA) >> 4, b_k = (16 * rowB) >> 4;
+    int s = 0;
+    uint32_t ph = 0, first = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
-        const uint32_t b_s = a_s + A_BYTES;
+        const uint32_t a_lo = desc_lo(a_s, slabA_bytes), b_lo = desc_lo(a_s + A_BYTES, slabB_bytes);
 #pragma unroll
-        for (int k = 0; k < KT / 16; ++k) {
-          // MN-major: LBO = distance between 64(32)-channel slabs, SBO = distance between groups of 8 pixels
-          const uint64_t da = smem_desc(a_s + k * 16 * rowA, slabA_bytes, 8 * rowA, layA);
-          const uint64_t db = smem_desc(b_s + k * 16 * rowB, slabB_bytes, 8 * rowB, layB);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0);
-        }
+        for (int k = 0; k < KT / 16; ++k)
+          umma_bf16_lohi(tmem_base, a_lo + k * a_k, a_hi, b_lo + k * b_k, b_hi, idesc, k ? 1u : first);
         umma_commit(empty_bar(s));
+        if (tile == t_end - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      first = 1;
+      if (++s == stages) { s = 0; ph ^= 1; }
     }
   } else if (t_begin < t_end) {
     const int q = warp & 3;

@@ -351,29 +351,46 @@ int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr,
   return phs_check_launch("momentum_step");
 }
 
-// bf16 shadows of the conv filters.  One block column per conv (blockIdx.y), grid-stride over its elements.
+// bf16 shadows of the conv filters.  blockIdx.y = conv, the blocks of a column walk its 32x32 (ci, co) tiles of every
+// tap: the dgrad layout keeps co contiguous (coalesced straight from the load), the forward layout is the per-tap
+// transpose and goes through shared memory so that both global accesses are coalesced.
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ master, bf16* __restrict__ shadow,
                                                           const int64_t* __restrict__ table) {
+  __shared__ float tile[32][33];
   const int64_t* e = table + (int64_t)blockIdx.y * 6;
   const float* src = master + e[0];
   bf16* fwd = shadow + e[1];
   bf16* dg = shadow + e[2];
-  int taps = (int)e[3], cin = (int)e[4], cout = (int)e[5];
-  int64_t total = (int64_t)taps * cin * cout;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int co = (int)(i % cout);
-    int64_t t = i / cout;
-    int ci = (int)(t % cin);
-    int tap = (int)(t / cin);
-    bf16 v = __float2bfloat16_rn(src[i]);  // src is HWIO: [tap][ci][co]
-    fwd[(int64_t)co * taps * cin + (int64_t)tap * cin + ci] = v;
-    dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = v;
+  const int taps = (int)e[3], cin = (int)e[4], cout = (int)e[5];
+  const int tci = (cin + 31) / 32, tco = (cout + 31) / 32;
+  const int ntiles = taps * tci * tco;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int co0 = (t % tco) * 32, ci0 = ((t / tco) % tci) * 32, tap = t / (tco * tci);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + ty + 8 * j, co = co0 + tx;
+      float v = 0.f;
+      if (ci < cin && co < cout) {
+        v = src[((int64_t)tap * cin + ci) * cout + co];   // HWIO: [tap][ci][co]
+        dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = __float2bfloat16_rn(v);
+      }
+      tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + ty + 8 * j, ci = ci0 + tx;
+      if (ci < cin && co < cout)
+        fwd[(int64_t)co * taps * cin + (int64_t)tap * cin + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+    }
+    __syncthreads();
   }
 }
 
 int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream) {
   PHS_REQUIRE(master && shadow && table, "phs_weight_prep: null argument");
   if (nconv <= 0) return 0;
-  weight_prep_kernel<<<dim3(8, nconv), 256, 0, (cudaStream_t)stream>>>(master, (bf16*)shadow, table);
+  weight_prep_kernel<<<dim3(48, nconv), 256, 0, (cudaStream_t)stream>>>(master, (bf16*)shadow, table);
   return phs_check_launch("weight_prep");
 }

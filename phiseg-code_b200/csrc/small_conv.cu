@@ -336,13 +336,11 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
   if (wd->ld % 8 != 0 || ((uintptr_t)wd->ptr % (8 * wes > 16 ? 16 : 8 * wes)) != 0) return 0;
   const int taps = ksize * ksize;
   const int pairs = taps * s->C * (wd->C / 8);
-  // PB pairs per block (a multiple of 32, at most 256); the other 256 / PB thread groups are pixel lanes
-  int PB = pairs >= 256 ? 256 : ((pairs + 31) / 32) * 32;
-  if (PB == 96) PB = 128;
-  if (PB > 128 && PB < 256) PB = 256;
+  // PB pairs per block (32 or 64); the other 256 / PB thread groups are pixel lanes over the block's pixel range
+  const int PB = pairs <= 32 ? 32 : 64;
   const int gy = (pairs + PB - 1) / PB;
   int64_t splits = (148 * 4 + gy - 1) / gy;
-  if (splits > (M + 255) / 256) splits = (M + 255) / 256;
+  if (splits > (M + 127) / 128) splits = (M + 127) / 128;
   if (splits < 1) splits = 1;
   const int64_t ppb = (M + splits - 1) / splits;
   splits = (M + ppb - 1) / ppb;
