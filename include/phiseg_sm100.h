@@ -117,14 +117,19 @@ int phs_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
 /* tf.train.MomentumOptimizer(momentum, use_nesterov=True) */
 int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr, const float* lr_dev, float momentum,
                       float grad_scale, void* stream);
-/* bf16 shadows of every conv filter for the tensor-core kernels.  table: int64[nconv][6] =
- * {src_off (floats into master), fwd_off, dgrad_off (bf16 elements into shadow), taps, cin, cout}.
+/* bf16 shadows of every conv filter for the tensor-core kernels.  table: int64[nconv][7] =
+ * {src_off (floats into master), fwd_off, dgrad_off (bf16 elements into shadow; < 0: no dgrad layout), taps, cin, cout,
+ *  kpitch (row pitch of the forward layout in elements; 0 = taps*cin; larger = rows zero padded by the caller)}.
  * fwd layout  [cout][tap*cin + ci]; dgrad layout [cin][(taps-1-tap)*cout + co]. */
 int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* dst[.., c_off + c] = src[.., c] with dtype conversion (strided channel-slice copy) */
 int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream);
+/* out[.., tap*Cin + ci] = x[.. shifted by tap .., ci] (zero outside the image), other channels 0; out bf16 with
+ * C >= 9*Cin.  Rewrites the 3x3 convolution of a 1..7-channel network input (posteriors.py:87, priors.py:80,
+ * likelihoods.py:110) as a 1x1 convolution over <= 64 channels for the tensor-core kernels. */
+int phs_im2col3x3(const phs_tensor* x, const phs_tensor* out, void* stream);
 /* posterior input tf.concat([x, one_hot(s) - 0.5], -1) (phiseg_model.py:29, posteriors.py:87) */
 int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, int Cx, int nlabels,
                         const phs_tensor* out, void* stream);

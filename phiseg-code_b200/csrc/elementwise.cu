@@ -184,11 +184,19 @@ int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* m
 // ---------------------------------------------------------------------------------------------------------
 // finalize kernels (tiny): one thread per channel (BN) or per (n, channel) (GN)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int HW, int C, int mode, float eps,
-                                     float decay, float* moving_mean, float* moving_var, float* __restrict__ mean,
-                                     float* __restrict__ rstd) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per channel (BN: lanes stride over the samples) or one thread per (n, c) (GN)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(128) norm_finalize_kernel(const float* __restrict__ stats, int N, int HW, int C,
+                                                            int mode, float eps, float decay, float* moving_mean,
+                                                            float* moving_var, float* __restrict__ mean,
+                                                            float* __restrict__ rstd) {
   if (mode == PHS_NORM_GN) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * C) return;
     int n = idx / C, c = idx % C;
     int G = max(2, C / 16);
@@ -205,35 +213,38 @@ __global__ void norm_finalize_kernel(const float* __restrict__ stats, int N, int
     if (var < 0) var = 0;
     mean[idx] = (float)m;
     rstd[idx] = (float)(1.0 / sqrt(var + (double)eps));
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  float m, r;
+  if (mode == PHS_NORM_BN_TRAIN) {
+    double s = 0.0, q = 0.0;
+    for (int n = lane; n < N; n += 32) {
+      s += stats[((size_t)n * C + c) * 2];
+      q += stats[((size_t)n * C + c) * 2 + 1];
+    }
+    s = warp_sum_d(s);
+    q = warp_sum_d(q);
+    double cnt = (double)HW * N;
+    double mm = s / cnt;
+    double var = q / cnt - mm * mm;
+    if (var < 0) var = 0;
+    m = (float)mm;
+    r = (float)(1.0 / sqrt(var + (double)eps));
+    if (moving_mean && lane == 0) {
+      double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+      moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * m;
+      moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)unb;
+    }
   } else {
-    if (idx >= C) return;
-    int c = idx;
-    float m, r;
-    if (mode == PHS_NORM_BN_TRAIN) {
-      double s = 0.0, q = 0.0;
-      for (int n = 0; n < N; ++n) {
-        s += stats[((size_t)n * C + c) * 2];
-        q += stats[((size_t)n * C + c) * 2 + 1];
-      }
-      double cnt = (double)HW * N;
-      double mm = s / cnt;
-      double var = q / cnt - mm * mm;
-      if (var < 0) var = 0;
-      m = (float)mm;
-      r = (float)(1.0 / sqrt(var + (double)eps));
-      if (moving_mean) {
-        double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
-        moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * m;
-        moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)unb;
-      }
-    } else {
-      m = moving_mean[c];
-      r = rsqrtf(moving_var[c] + eps);
-    }
-    for (int n = 0; n < N; ++n) {
-      mean[(size_t)n * C + c] = m;
-      rstd[(size_t)n * C + c] = r;
-    }
+    m = moving_mean[c];
+    r = rsqrtf(moving_var[c] + eps);
+  }
+  for (int n = lane; n < N; n += 32) {
+    mean[(size_t)n * C + c] = m;
+    rstd[(size_t)n * C + c] = r;
   }
 }
 
@@ -243,9 +254,9 @@ int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float 
   PHS_REQUIRE(mode == PHS_NORM_BN_INFER || stats, "phs_norm_finalize: stats required");
   PHS_REQUIRE(mode != PHS_NORM_BN_INFER || (moving_mean && moving_var), "phs_norm_finalize: moving stats required");
   PHS_REQUIRE(mode != PHS_NORM_GN || C % max(2, C / 16) == 0, "phs_norm_finalize: C=%d not divisible into groups", C);
-  int total = mode == PHS_NORM_GN ? N * C : C;
-  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, N, HW, C, mode, eps, decay,
-                                                                            moving_mean, moving_var, mean, rstd);
+  int blocks = mode == PHS_NORM_GN ? (N * C + 127) / 128 : (C + 3) / 4;
+  norm_finalize_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(stats, N, HW, C, mode, eps, decay, moving_mean,
+                                                                 moving_var, mean, rstd);
   return phs_check_launch("norm_finalize");
 }
 
@@ -254,24 +265,28 @@ int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float 
 //   BN: m1[c] = gamma*sum_n s1/(N*HW), m2[c] = gamma*sum_n s2/(N*HW)
 //   GN: m1[n,grp] = sum_{c in grp} gamma_c*s1/(cpg*HW), m2 likewise
 //   dx = rstd*(g'*gamma - m1 - xhat*m2);   dbias[c] = sum_{n,hw} dx  (closed form from the forward sums)
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
-                                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                                         const float* __restrict__ gamma, int N, int HW, int C, int mode,
-                                         float* __restrict__ coef, float* dgamma, float* dbeta, float* dbias,
-                                         int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel, lanes stride over the samples
+__global__ void __launch_bounds__(128)
+    norm_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
+                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                             const float* __restrict__ gamma, int N, int HW, int C, int mode, float* __restrict__ coef,
+                             float* dgamma, float* dbeta, float* dbias, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double a1 = 0.0, a2 = 0.0, db = 0.0;
-  for (int n = 0; n < N; ++n) {
+  for (int n = lane; n < N; n += 32) {
     a1 += sums[((size_t)n * C + c) * 2];
     a2 += sums[((size_t)n * C + c) * 2 + 1];
   }
-  float ga = gamma[c];
+  a1 = warp_sum_d(a1);
+  a2 = warp_sum_d(a2);
+  const float ga = gamma[c];
   if (mode == PHS_NORM_GN) {
-    int G = max(2, C / 16);
-    int cpg = C / G;
-    int c0 = (c / cpg) * cpg;
-    for (int n = 0; n < N; ++n) {
+    const int G = max(2, C / 16);
+    const int cpg = C / G;
+    const int c0 = (c / cpg) * cpg;
+    for (int n = lane; n < N; n += 32) {
       double m1 = 0.0, m2 = 0.0;
       for (int i = 0; i < cpg; ++i) {
         float gi = gamma[c0 + i];
@@ -289,18 +304,21 @@ __global__ void norm_bwd_finalize_kernel(const float* __restrict__ sums, const f
         db += r * ((double)ga * sums[((size_t)n * C + c) * 2] - (double)HW * m1 - m2 * sx);
       }
     }
+    db = warp_sum_d(db);
   } else {
     double cnt = (double)HW * N;
     double m1 = ga * a1 / cnt, m2 = ga * a2 / cnt;
-    for (int n = 0; n < N; ++n) {
+    for (int n = lane; n < N; n += 32) {
       coef[((size_t)n * C + c) * 2] = (float)m1;
       coef[((size_t)n * C + c) * 2 + 1] = (float)m2;
     }
     db = 0.0;  // batch norm removes any per-channel offset: the bias gradient is exactly zero
   }
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)a2;
-  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)a1;
-  if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)db;
+  if (lane == 0) {
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)a2;
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)a1;
+    if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + (float)db;
+  }
 }
 
 int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* mean, const float* rstd,
@@ -309,8 +327,8 @@ int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* me
   PHS_REQUIRE(sums && mean && rstd && gamma && coef, "phs_norm_bwd_finalize: null argument");
   PHS_REQUIRE(!dbias || stats, "phs_norm_bwd_finalize: dbias needs the forward stats");
   PHS_REQUIRE(mode == PHS_NORM_GN || mode == PHS_NORM_BN_TRAIN, "phs_norm_bwd_finalize: mode %d has no backward", mode);
-  norm_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sums, stats, mean, rstd, gamma, N, HW, C, mode,
-                                                                         coef, dgamma, dbeta, dbias, accumulate);
+  norm_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(sums, stats, mean, rstd, gamma, N, HW, C, mode,
+                                                                        coef, dgamma, dbeta, dbias, accumulate);
   return phs_check_launch("norm_bwd_finalize");
 }
 
@@ -725,6 +743,46 @@ int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, i
   PHS_DISPATCH_DTYPE(out->dtype, T, (posterior_input_kernel<T><<<stream_blocks(npix), 256, 0, (cudaStream_t)stream>>>(
                                         x, s, Cx, nlabels, (T*)out->ptr, out->ld, npix)));
   return phs_check_launch("posterior_input");
+}
+
+// out[p][tap*Cin + ci] = x[p + tap][ci] (zero outside the image), remaining channels of out = 0.  Turns the 3x3
+// convolution of a 1..7-channel network input into a 1x1 convolution over <= 64 channels that the tensor-core kernels
+// take (forward and filter gradient); one thread per (pixel, 8-channel output vector).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ x, int ldx, int Cin, bf16* __restrict__ out,
+                                                        int ldo, int Co, int H, int W, int64_t total) {
+  const int nvec = Co / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int64_t pix = i / nvec;
+    const int wq = (int)(pix % W);
+    const int hq = (int)((pix / W) % H);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      const int tap = k / Cin, ci = k - tap * Cin;
+      float val = 0.f;
+      if (tap < 9) {
+        const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = ldf<T>(x + (pix + (int64_t)(hh - hq) * W + (ww - wq)) * ldx + ci);
+      }
+      o[j] = val;
+    }
+    stv<bf16, 8>(out + pix * ldo + v * 8, o);
+  }
+}
+
+int phs_im2col3x3(const phs_tensor* x, const phs_tensor* out, void* stream) {
+  PHS_REQUIRE(x && out && x->ptr && out->ptr, "phs_im2col3x3: null argument");
+  PHS_REQUIRE(out->dtype == PHS_BF16 && out->C % 8 == 0 && out->ld % 8 == 0 && ((uintptr_t)out->ptr & 15) == 0,
+              "phs_im2col3x3: output must be bf16 with 16-byte aligned 8-channel vectors");
+  PHS_REQUIRE(out->C >= 9 * x->C && x->N == out->N && x->H == out->H && x->W == out->W,
+              "phs_im2col3x3: output needs >= 9*Cin channels and the input's N,H,W");
+  int64_t total = (int64_t)x->N * x->H * x->W * (out->C / 8);
+  PHS_DISPATCH_DTYPE(x->dtype, T, (im2col3x3_kernel<T><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                                      (const T*)x->ptr, x->ld, x->C, (bf16*)out->ptr, out->ld, out->C, x->H, x->W, total)));
+  return phs_check_launch("im2col3x3");
 }
 
 template <typename T>

@@ -357,11 +357,12 @@ int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr,
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ master, bf16* __restrict__ shadow,
                                                           const int64_t* __restrict__ table) {
   __shared__ float tile[32][33];
-  const int64_t* e = table + (int64_t)blockIdx.y * 6;
+  const int64_t* e = table + (int64_t)blockIdx.y * 7;
   const float* src = master + e[0];
   bf16* fwd = shadow + e[1];
-  bf16* dg = shadow + e[2];
+  bf16* dg = e[2] >= 0 ? shadow + e[2] : nullptr;
   const int taps = (int)e[3], cin = (int)e[4], cout = (int)e[5];
+  const int64_t kpitch = e[6] > 0 ? e[6] : (int64_t)taps * cin;   // row pitch of the forward layout (zero padded)
   const int tci = (cin + 31) / 32, tco = (cout + 31) / 32;
   const int ntiles = taps * tci * tco;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
       float v = 0.f;
       if (ci < cin && co < cout) {
         v = src[((int64_t)tap * cin + ci) * cout + co];   // HWIO: [tap][ci][co]
-        dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = __float2bfloat16_rn(v);
+        if (dg) dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = __float2bfloat16_rn(v);
       }
       tile[ty + 8 * j][tx] = v;
     }
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
     for (int j = 0; j < 4; ++j) {
       const int co = co0 + ty + 8 * j, ci = ci0 + tx;
       if (ci < cin && co < cout)
-        fwd[(int64_t)co * taps * cin + (int64_t)tap * cin + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+        fwd[(int64_t)co * kpitch + (int64_t)tap * cin + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
     }
     __syncthreads();
   }

@@ -161,6 +161,11 @@ def tc_eligible(k, cin, cout):
     return cin % 32 == 0 and cout % 32 == 0 and cout <= 256
 
 
+def pad_eligible(k, cin, cout):
+    """3x3 convs of a 1..7-channel tensor that can run as im2col + 1x1 tensor-core conv (no input gradient)."""
+    return k == 3 and cin <= 7 and cout % 32 == 0 and cout <= 256
+
+
 class Params:
     """Flat fp32 master / gradient / optimizer-slot buffers addressed through a name table, plus the BN moving
     statistics and (fast mode) the bf16 filter shadows the tensor-core kernels read."""
@@ -188,6 +193,7 @@ class Params:
         self.shadow = None
         self.shadow_table = {}
         self.prep_table = None
+        self.pad_table = {}
         if cfg.mode == 'fast':
             rows, soff = [], 0
             for name, shape, kind in self.spec:
@@ -195,10 +201,17 @@ class Params:
                     n = int(np.prod(shape))
                     taps = shape[0] * shape[1]
                     self.shadow_table[name] = (soff, soff + n)
-                    rows.append([self.table[name][0], soff, soff + n, taps, shape[2], shape[3]])
+                    rows.append([self.table[name][0], soff, soff + n, taps, shape[2], shape[3], 0])
                     soff += 2 * n
+                elif kind == 'W' and pad_eligible(shape[0], shape[2], shape[3]):
+                    # network-input convs: im2col'ed 1x1 form, K = 9*cin zero padded to kp (phs_im2col3x3)
+                    k9 = 9 * shape[2]
+                    kp = 32 if k9 <= 32 else 64
+                    self.pad_table[name] = (soff, kp)
+                    rows.append([self.table[name][0], soff, -1, 1, k9, shape[3], kp])
+                    soff += kp * shape[3]
             self.shadow = torch.zeros(max(soff, 8), dtype=torch.bfloat16, device=device)
-            self.prep_table = torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1, 6)
+            self.prep_table = torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1, 7)
         self.init()
 
     # -- views ------------------------------------------------------------------------------------------
@@ -221,6 +234,9 @@ class Params:
     def shadow_ptr(self, name, dgrad):
         off = self.shadow_table[name][1 if dgrad else 0]
         return self.shadow.data_ptr() + 2 * off
+
+    def pad_shadow_ptr(self, name):
+        return self.shadow.data_ptr() + 2 * self.pad_table[name][0]
 
     def names(self):
         return [n for n, _, _ in self.spec]
@@ -403,10 +419,21 @@ class Builder:
         bias = P.ptr(scope + '/b') if P.has(scope + '/b') else None
         tc = (cfg.mode == 'fast' and tc_eligible(k, cin, cout) and x.dtype == L.PHS_BF16
               and (out_dtype in (None, L.PHS_BF16)))
-        impl = L.IMPL_TC if tc else L.IMPL_SIMT
-        w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
-        w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
         self.n_conv_flop += 2 * x.N * x.H * x.W * k * k * cin * cout
+        # network inputs (no input gradient): im2col once, then a 1x1 tensor-core conv forward and in the filter gradient
+        pad_in = (cfg.mode == 'fast' and not need_dx and wname in P.pad_table and out_dtype in (None, L.PHS_BF16))
+        k_real, cin_real, x_real = k, cin, x
+        if pad_in:
+            kp = P.pad_table[wname][1]
+            xcol = self.new(x.N, x.H, x.W, kp, L.PHS_BF16)
+            self.emit('phs_im2col3x3', x.desc(), xcol.desc())
+            x, k, cin, tc = xcol, 1, kp, True
+        impl = L.IMPL_TC if tc else L.IMPL_SIMT
+        if pad_in:
+            w_f = w_d = P.pad_shadow_ptr(wname)
+        else:
+            w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
+            w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
         ydt = self.adt if out_dtype is None else out_dtype
         if not normed:
             y = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
@@ -463,7 +490,12 @@ class Builder:
                 else:
                     dy = ga
                     db = P.ptr(scope + '/b', 'g') if bias is not None else None
-                self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
+                if pad_in:
+                    scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
+                    self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
+                    self.emit('phs_axpy_f32', P.ptr(wname, 'g'), scratch.data_ptr(), 9 * cin_real * cout, 1.0)
+                else:
+                    self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
                 if need_dx:
                     gx = x.grad()
                     acc = int(x.grad_written())

@@ -50,6 +50,7 @@ SIGNATURES = {
     'phs_momentum_step': [_P, _P, _P, c_int64, c_float, _P, c_float, c_float, _S],
     'phs_weight_prep': [_P, _P, _P, c_int, _S],
     'phs_copy_cast': [_T, _T, _S],
+    'phs_im2col3x3': [_T, _T, _S],
     'phs_posterior_input': [_P, _P, c_int, c_int, c_int, c_int, c_int, _T, _S],
     'phs_broadcast_z': [_P, _T, _S],
     'phs_broadcast_z_bwd': [_T, _P, c_int, _S],

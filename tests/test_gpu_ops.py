@@ -361,3 +361,23 @@ def test_small_helpers(call, lib):
     dst = torch.zeros(2, 4, 4, 16, dtype=torch.bfloat16, device='cuda')
     call('phs_copy_cast', call.T(src), call.T(dst, 8, 8))
     assert torch.equal(dst[..., 8:].float(), src.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize('Cin,Co,dt', [(3, 32, torch.bfloat16), (1, 32, torch.float32), (5, 64, torch.bfloat16)])
+def test_im2col3x3(call, lib, oracle, Cin, Co, dt):
+    """phs_im2col3x3 followed by a 1x1 convolution with the HWIO filter flattened to [9*Cin, Cout] equals the 3x3 SAME
+    convolution (tfwrapper/layers.py:123) of the network input"""
+    g = torch.Generator().manual_seed(Cin + Co)
+    x = torch.randn(2, 16, 8, Cin, generator=g).to(dt)
+    xd = x.cuda()
+    col = torch.full((2, 16, 8, Co), 7.0, device='cuda', dtype=torch.bfloat16)
+    call('phs_im2col3x3', call.T(xd), call.T(col))
+    w = torch.randn(3, 3, Cin, 4, generator=g, dtype=torch.float64)
+    ref = oracle.conv2d_same(x.double(), w)
+    wf = torch.zeros(Co, 4, dtype=torch.float64)
+    wf[:9 * Cin] = w.reshape(9 * Cin, 4)
+    got = col.double().cpu() @ wf
+    close(got, ref, rtol=1e-2 if dt == torch.bfloat16 else 1e-2, what='im2col conv')
+    assert float(col[..., 9 * Cin:].float().abs().max()) == 0.0
+    # exactness of the gather itself: centre tap reproduces x
+    assert torch.equal(col[..., 4 * Cin:5 * Cin].float().cpu(), x.to(torch.bfloat16).float())
