@@ -36,6 +36,8 @@ CONFIGS = {
     'phiseg_7_5_256': ('phiseg_7_5_256', 32, 256, 4),
 }
 CPU_BATCH = 12   # phiseg/experiments/phiseg_7_5.py:38
+# DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/conv_halo_r01.txt)
+NCU_TRAFFIC = {'128x128 128->128 k3': None}
 
 
 def measured_peaks():
@@ -224,6 +226,35 @@ def main():
     dt_e2e = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- the dominant kernel alone (largest-FLOP convolution launch of the step), CUDA events on the launching stream
+    kern = None
+    if rank == 0:
+        best = None
+        for fn, a, name in sp.prog.steps:
+            if fn is not None and name in ('phs_conv2d_stats', 'phs_conv2d'):
+                xd, yd, k = a[0]._obj, a[3]._obj, a[4]
+                fl = 2.0 * xd.N * xd.H * xd.W * k * k * xd.C * yd.C
+                if best is None or fl > best[0]:
+                    best = (fl, fn, a, name, '%dx%d %d->%d k%d' % (xd.H, xd.W, xd.C, yd.C, k),
+                            (xd.N * xd.H * xd.W * (xd.C + yd.C) * 2 + k * k * xd.C * yd.C * 2))
+        if best is not None:
+            fl, fn, a, name, shape, alg_bytes = best
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(3):
+                fn(*a, st)
+            ts = []
+            for _ in range(10):
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                fn(*a, st)
+                k1.record()
+                torch.cuda.synchronize()
+                ts.append(k0.elapsed_time(k1) * 1e-3)
+            kt = sum(ts) / len(ts)
+            kern = (fl, kt, name, shape, alg_bytes)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     peak_tf, peak_hbm, peak_src = measured_peaks()
@@ -252,6 +283,19 @@ def main():
                              '%.2f algorithmic GFLOP/image x %d images / step time; peak = %s'
                              % (flop_step / batch / 1e9, batch, peak_src)},
     }
+    if kern is not None:
+        fl, kt, name, shape, alg_bytes = kern
+        burst = 1696.6
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            burst = json.load(open(pk)).get('bf16_tflops', burst)
+        line['roofline_kernel'] = {
+            'kernel': 'conv_halo_kernel<64> via %s, %s, batch %d (the largest convolution launch of the step)' % (name, shape, batch),
+            'bound': 'tensor', 'achieved': fl / kt / 1e12, 'peak': burst, 'unit': 'TFLOP/s', 'frac': fl / kt / 1e12 / burst,
+            'us_per_launch': kt * 1e6, 'algorithmic_bytes': alg_bytes,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/conv_halo_r01.txt (ncu --set full)
+            'traffic': NCU_TRAFFIC.get(shape),
+            'peak_source': 'measured burst bf16 (MEASURED_PEAKS.json): kernel timed alone'}
     if world == 1 and not args.no_cpu:
         ips, sps, cores = run_cpu_oracle(2, 1)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

@@ -12,6 +12,7 @@ the RNG for eps and torch.distributed; every arithmetic step of the path is a ke
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -352,6 +353,11 @@ class Act:
         self.buf.gw = [(a, b) for a, b in self.buf.gw if not (lo <= a and b <= hi)] + [(lo, hi)]
 
 
+class Step(tuple):
+    """(fn, args, name) of one C-ABI launch, plus the lane (stream) it is enqueued on."""
+    lane = 0
+
+
 class Program:
     """A replayable list of kernel launches."""
 
@@ -363,8 +369,16 @@ class Program:
         self.lib = L.load()
         self.graph = None
 
-    def emit(self, name, *args):
-        self.steps.append((getattr(self.lib, name), args, name))
+    def emit(self, name, *args, lane=0):
+        st = Step((getattr(self.lib, name), args, name))
+        st.lane = lane
+        self.steps.append(st)
+
+    def emit_sync(self, kind, lanes):
+        """'fork': the side lanes wait for everything enqueued so far on lane 0; 'join': lane 0 waits for the side lanes."""
+        st = Step((None, (tuple(lanes),), kind))
+        st.lane = 0
+        self.steps.append(st)
 
     def vec(self, n, zero=False):
         t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=self.device)
@@ -373,14 +387,42 @@ class Program:
         return t
 
     def run_eager(self, steps=None):
-        st = torch.cuda.current_stream().cuda_stream
-        for fn, args, name in (self.steps if steps is None else steps):
-            rc = fn(*args, st)
+        """Enqueue the launches.  Lane 0 is the current stream; independent sub-graphs (the posterior and prior
+        encoders, the likelihood towers) are emitted on side lanes = side streams, forked from / joined to lane 0
+        with events.  Under CUDA-graph capture the same calls become parallel branches of the graph, which is what lets
+        the many small launches of the coarse pyramid levels overlap."""
+        main = torch.cuda.current_stream()
+        streams = {0: main}
+        for step in (self.steps if steps is None else steps):
+            fn, args, name = step
+            if fn is None:
+                for ln in args[0]:
+                    if ln not in streams:
+                        streams[ln] = self._side_stream(ln)
+                    ev = torch.cuda.Event()
+                    if name == 'fork':
+                        ev.record(main)
+                        streams[ln].wait_event(ev)
+                    else:
+                        ev.record(streams[ln])
+                        main.wait_event(ev)
+                continue
+            lane = getattr(step, 'lane', 0)
+            if lane not in streams:
+                raise RuntimeError('launch on lane %d outside a fork/join region' % lane)
+            rc = fn(*args, streams[lane].cuda_stream)
             if rc:
                 L.check(rc, name)
 
-    def launches(self):
-        return len(self.steps)
+    def _side_stream(self, lane):
+        if not hasattr(self, '_sides'):
+            self._sides = {}
+        if lane not in self._sides:
+            self._sides[lane] = torch.cuda.Stream(device=self.device)
+        return self._sides[lane]
+
+    def launches(self, steps=None):
+        return sum(1 for s in (self.steps if steps is None else steps) if s[0] is not None)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -397,13 +439,38 @@ class Builder:
         self.tape = []
         self.adt = L.PHS_BF16 if cfg.mode == 'fast' else L.PHS_F32      # activation dtype
         self.n_conv_flop = 0
+        self.lane = 0
+        self.use_lanes = os.environ.get('PHS_NO_LANES') is None
 
     # -- helpers ------------------------------------------------------------------------------------------
     def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
         return Buf(self.prog, N, H, W, C if ld is None else ld, self.adt if dtype is None else dtype, zero).act(0, C)
 
     def emit(self, name, *args):
-        self.prog.emit(name, *args)
+        self.prog.emit(name, *args, lane=self.lane)
+
+    # -- concurrency regions: fork() ... work on several lanes ... join(); the adjoints mirror them in reverse ---
+    def fork(self, lanes):
+        if not self.use_lanes:
+            return
+        self.prog.emit_sync('fork', lanes)
+        if self.want_grad:
+            self.tape.append(('join', tuple(lanes)))
+
+    def join(self, lanes):
+        if not self.use_lanes:
+            return
+        self.lane = 0
+        self.prog.emit_sync('join', lanes)
+        if self.want_grad:
+            self.tape.append(('fork', tuple(lanes)))
+
+    def set_lane(self, lane):
+        self.lane = lane if self.use_lanes else 0
+
+    def push_bwd(self, fn):
+        fn.lane = self.lane
+        self.tape.append(fn)
 
     def _norm_mode(self):
         if self.cfg.norm == 'group_norm':
@@ -501,7 +568,7 @@ class Builder:
                     acc = int(x.grad_written())
                     self.emit('phs_conv2d', dy.desc(), w_d, None, gx.desc(), k, 1, acc, impl)
                     x.mark_grad_written()
-            self.tape.append(bwd)
+            self.push_bwd(bwd)
         return a
 
     # -- layers.averagepool2D (tfwrapper/layers.py:44-54) ---------------------------------------------------
@@ -513,7 +580,7 @@ class Builder:
                 assert y.grad_written()
                 self.emit('phs_avgpool2_bwd', y.grad().desc(), x.grad().desc(), int(x.grad_written()))
                 x.mark_grad_written()
-            self.tape.append(bwd)
+            self.push_bwd(bwd)
         return y
 
     # -- layers.bilinear_upsample2D (tfwrapper/layers.py:336-345) -------------------------------------------
@@ -525,12 +592,18 @@ class Builder:
                 assert y.grad_written()
                 self.emit('phs_upsample2_bwd', y.grad().desc(), x.grad().desc(), int(x.grad_written()))
                 x.mark_grad_written()
-            self.tape.append(bwd)
+            self.push_bwd(bwd)
         return y
 
     def emit_backward(self):
         for f in reversed(self.tape):
+            if isinstance(f, tuple):            # mirrored concurrency region
+                self.lane = 0
+                self.prog.emit_sync(f[0], f[1])
+                continue
+            self.lane = getattr(f, 'lane', 0)
             f()
+        self.lane = 0
         self.tape = []
 
 
@@ -596,7 +669,11 @@ def build_program(cfg, params, B, kind, device):
             # straight into the first channels of their concat buffer (tf.concat at posteriors.py:120 is free)
             pre_z = {}
             cat = {}
-            for net, inp in nets:
+            two = len(nets) == 2
+            if two:
+                b.fork([1])
+            for li, (net, inp) in enumerate(nets):
+                b.set_lane(li if two else 0)
                 h = inp
                 for r in range(R):
                     if r > 0:
@@ -611,6 +688,8 @@ def build_program(cfg, params, B, kind, device):
                         out = cbuf.act(0, nc[r])
                     h = b.conv(h, '%s/z%d_pre_3' % (net, r), 3, nc[r], out=out)
                     pre_z[(net, r)] = h
+            if two:
+                b.join([1])
             # --- latent hierarchy, posterior and prior level by level (posteriors.py:98-130, priors.py:92-126)
             mu = {n: [None] * Lv for n, _ in nets}
             spre = {n: [None] * Lv for n, _ in nets}
@@ -731,7 +810,7 @@ def _emit_latent(b, sp, l, hw, mu, spre, sig, z, gen_mode, need_post, need_prior
                     *[o.grad().ptr for o in outs])
             for o in outs:
                 o.mark_grad_written()
-        b.tape.append(bwd)
+        b.push_bwd(bwd)
 
 
 def _phiseg_likelihood(b, cfg, z):
@@ -743,7 +822,12 @@ def _phiseg_likelihood(b, cfg, z):
     B, H, W = b.B, cfg.H, cfg.W
     post_z, post_c = [None] * Lv, [None] * Lv
     cat = [None] * Lv
+    # the per-level towers only depend on their own z: coarse levels (small, latency-bound launches) on a side lane
+    towers = Lv > 2
+    if towers:
+        b.fork([1])
     for i in range(Lv):
+        b.set_lane(1 if (towers and i >= 2) else 0)
         h = b.conv(z[i], 'likelihood/z%d_post_1' % i, 3, nc[i])
         h = b.conv(h, 'likelihood/z%d_post_2' % i, 3, nc[i])
         for t in range(d):
@@ -754,6 +838,8 @@ def _phiseg_likelihood(b, cfg, z):
                 out = cat[i].act(0, nc[i])
             h = b.conv(h, 'likelihood/preups_%d/z%d_post' % (i, t), 3, nc[i], out=out)
         post_z[i] = h
+    if towers:
+        b.join([1])
     post_c[Lv - 1] = post_z[Lv - 1]
     for i in reversed(range(Lv - 1)):
         u = b.up(post_c[i + 1])
@@ -806,7 +892,7 @@ def _probunet_likelihood(b, cfg, z, x):
         def bwd():
             pr.emit('phs_broadcast_z_bwd', zs.grad().desc(), z.grad().ptr, int(z.grad_written()))
             z.mark_grad_written()
-        b.tape.append(bwd)
+        b.push_bwd(bwd)
     h = rc.act()
     for t in range(3):
         h = b.conv(h, 'likelihood/recomb_%d' % t, 1, nc[0])

@@ -150,7 +150,7 @@ class phiseg():
         """Replay a launch list: eagerly the first time (loads modules, validates arguments), then from a CUDA
         graph captured on the second call."""
         pr = sp.prog
-        self.gpu_launches += len(steps)
+        self.gpu_launches += pr.launches(steps)
         if not self.use_cuda_graph:
             pr.run_eager(steps)
             return

@@ -35,7 +35,7 @@ def main():
         model.training_step(x, s, 1e-3)
     sp = model._program('train', args.batch)
     st = torch.cuda.current_stream().cuda_stream
-    steps = sp.prog.steps
+    steps = [s_ for s_ in sp.prog.steps if s_[0] is not None]
     times = [[] for _ in steps]
     for rep in range(args.reps):
         evs = []
@@ -78,6 +78,20 @@ def main():
             by_shape[key][0] += t
             by_shape[key][1] += 1
             by_shape[key][2] += fl
+    # memory-bound kernels by tensor shape: achieved GB/s against the passes they make
+    passes = {'phs_norm_act_fwd': (0, 2), 'phs_norm_bwd_reduce': (0, 2), 'phs_norm_bwd_apply': (0, 3), 'phs_chan_stats': (0, 1),
+              'phs_upsample2_fwd': (1, 1.25), 'phs_upsample2_bwd': (0, 1.25), 'phs_avgpool2_fwd': (0, 1.25),
+              'phs_avgpool2_bwd': (1, 1.25)}
+    by_mem = collections.defaultdict(lambda: [0.0, 0, 0.0])
+    for (fn, a, name), t in zip(steps, med):
+        if name in passes:
+            ai, np_ = passes[name]
+            td = a[ai]._obj
+            nbytes = td.N * td.H * td.W * td.C * (2 if td.dtype == 1 else 4) * np_
+            key = '%s %dx%d C=%d' % (name, td.H, td.W, td.C)
+            by_mem[key][0] += t
+            by_mem[key][1] += 1
+            by_mem[key][2] += nbytes
     total = sum(med)
     print('total of per-launch medians: %.3f ms over %d launches (B=%d)' % (total / 1e3, len(steps), args.batch))
     print('\n-- by C-ABI entry point')
@@ -86,6 +100,9 @@ def main():
     print('\n-- convolutions by shape (top %d)' % args.top)
     for k, (t, n, fl) in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:args.top]:
         print('%-40s x%-2d %9.1f us %5.1f%%  %7.1f TFLOP/s' % (k, n, t, 100 * t / total, fl / t / 1e6))
+    print('\n-- memory-bound kernels by shape (top %d)' % args.top)
+    for k, (t, n, nb) in sorted(by_mem.items(), key=lambda kv: -kv[1][0])[:args.top]:
+        print('%-44s x%-2d %9.1f us %5.1f%%  %7.0f GB/s' % (k, n, t, 100 * t / total, nb / t / 1e3))
     if args.out:
         with open(args.out, 'w') as fh:
             json.dump({'total_us': total, 'by_kernel': {k: v for k, v in by_kernel.items()},
