@@ -595,6 +595,23 @@ class Builder:
             self.push_bwd(bwd)
         return y
 
+    # -- identity with its own gradient buffer: lets a consumer on another lane write "its" dz without racing the
+    #    other consumers of x; the adjoint folds the copy's gradient back into x's
+    def copy(self, x):
+        y = self.new(x.N, x.H, x.W, x.C, x.dtype)
+        self.emit('phs_copy_cast', x.desc(), y.desc())
+        if self.want_grad:
+            def bwd():
+                assert y.grad_written()
+                if x.grad_written():
+                    assert x.dtype == L.PHS_F32 and x.buf.ld == x.C and x.c_off == 0
+                    self.emit('phs_axpy_f32', x.grad().ptr, y.grad().ptr, x.N * x.H * x.W * x.C, 1.0)
+                else:
+                    self.emit('phs_copy_cast', y.grad().desc(), x.grad().desc())
+                    x.mark_grad_written()
+            self.push_bwd(bwd)
+        return y
+
     def emit_backward(self):
         for f in reversed(self.tape):
             if isinstance(f, tuple):            # mirrored concurrency region
@@ -695,16 +712,22 @@ def build_program(cfg, params, B, kind, device):
             spre = {n: [None] * Lv for n, _ in nets}
             sig = {n: [None] * Lv for n, _ in nets}
             zl = [None] * Lv
+            early = need_lik and b.use_lanes            # likelihood tower l starts as soon as z_l exists (lane 2)
+            post_z, lcat = [None] * Lv, [None] * Lv
             for l in reversed(range(Lv)):
                 hl, wl = H >> (l + d), W >> (l + d)
-                for net, _ in nets:
+                # the x2 up-sampling of z_{l+1} stays on lane 0: both nets' adjoints accumulate into the same dz
+                ups = {net: b.up(zl[l + 1]) for net, _ in nets} if l < Lv - 1 else {}
+                if two:
+                    b.fork([1])
+                for li, (net, _) in enumerate(nets):
+                    b.set_lane(li if two else 0)
                     if l == Lv - 1:
                         src = pre_z[(net, l + d)]
                         mu[net][l] = b.conv(src, '%s/z%d_mu' % (net, l), 3, zd, normed=False, out_dtype=f32)
                         spre[net][l] = b.conv(src, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
                     else:
-                        u = b.up(zl[l + 1])
-                        u = b.conv(u, '%s/z%d_ups_to_%d_c_1' % (net, l + 1, l + 1), 3, zd * cfg.n0)
+                        u = b.conv(ups[net], '%s/z%d_ups_to_%d_c_1' % (net, l + 1, l + 1), 3, zd * cfg.n0)
                         cbuf = cat[(net, l)]
                         b.conv(u, '%s/z%d_ups_to_%d_c_2' % (net, l + 1, l + 1), 3, zd * cfg.n0,
                                out=cbuf.act(nc[l + d], zd * cfg.n0))
@@ -713,8 +736,20 @@ def build_program(cfg, params, B, kind, device):
                         mu[net][l] = b.conv(zin, '%s/z%d_mu' % (net, l), 1, zd, normed=False, out_dtype=f32)
                         spre[net][l] = b.conv(zin, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
                     sig[net][l] = b.new(B, hl, wl, zd, f32)
+                if two:
+                    b.join([1])
+                b.set_lane(0)
                 zl[l] = b.new(B, hl, wl, zd, f32)
                 _emit_latent(b, sp, l, hl * wl, mu, spre, sig, zl[l], gen_mode, need_post, need_prior, gap=0)
+                if early:
+                    zt = b.copy(zl[l])
+                    b.fork([2])
+                    b.set_lane(2)
+                    post_z[l] = _phiseg_tower(b, cfg, l, zt, lcat)
+                    b.set_lane(0)
+            if early:
+                b.join([2])
+                sp.logits = _phiseg_merge(b, cfg, post_z, lcat)
             sp.z = zl
             if need_post:
                 sp.mu, sp.sigma = mu['posterior'], sig['posterior']
@@ -722,7 +757,7 @@ def build_program(cfg, params, B, kind, device):
                 sp.prior_mu, sp.prior_sigma = mu['prior'], sig['prior']
         else:
             sp.z = [b.new(*shapes[l], f32) for l in range(Lv)]          # fed by the caller ('from_z')
-        if need_lik:
+        if need_lik and not (nets and b.use_lanes):
             sp.logits = _phiseg_likelihood(b, cfg, sp.z)
     else:
         if nets:
@@ -813,45 +848,56 @@ def _emit_latent(b, sp, l, hw, mu, spre, sig, z, gen_mode, need_post, need_prior
         b.push_bwd(bwd)
 
 
-def _phiseg_likelihood(b, cfg, z):
-    """likelihoods.phiseg (likelihoods.py:162-223).  Returns native-resolution head outputs (the nearest-neighbour
-    resize of :221 is folded into the loss / aggregation kernels)."""
+def _phiseg_tower(b, cfg, i, z_i, cat):
+    """Level i of likelihoods.phiseg before the top-down merge (likelihoods.py:196-199): z_i -> 2 convs -> d x
+    [up-sample -> conv]; the last conv writes into the first half of the level's concat buffer."""
     nc, Lv, R = cfg.nc, cfg.L, cfg.R
     d = R - Lv
-    pr = b.prog
-    B, H, W = b.B, cfg.H, cfg.W
-    post_z, post_c = [None] * Lv, [None] * Lv
-    cat = [None] * Lv
-    # the per-level towers only depend on their own z: coarse levels (small, latency-bound launches) on a side lane
-    towers = Lv > 2
-    if towers:
-        b.fork([1])
-    for i in range(Lv):
-        b.set_lane(1 if (towers and i >= 2) else 0)
-        h = b.conv(z[i], 'likelihood/z%d_post_1' % i, 3, nc[i])
-        h = b.conv(h, 'likelihood/z%d_post_2' % i, 3, nc[i])
-        for t in range(d):
-            h = b.up(h)
-            out = None
-            if t == d - 1 and i < Lv - 1:
-                cat[i] = Buf(pr, B, h.H, h.W, 2 * nc[i], b.adt)
-                out = cat[i].act(0, nc[i])
-            h = b.conv(h, 'likelihood/preups_%d/z%d_post' % (i, t), 3, nc[i], out=out)
-        post_z[i] = h
-    if towers:
-        b.join([1])
+    h = b.conv(z_i, 'likelihood/z%d_post_1' % i, 3, nc[i])
+    h = b.conv(h, 'likelihood/z%d_post_2' % i, 3, nc[i])
+    for t in range(d):
+        h = b.up(h)
+        out = None
+        if t == d - 1 and i < Lv - 1:
+            cat[i] = Buf(b.prog, b.B, h.H, h.W, 2 * nc[i], b.adt)
+            out = cat[i].act(0, nc[i])
+        h = b.conv(h, 'likelihood/preups_%d/z%d_post' % (i, t), 3, nc[i], out=out)
+    return h
+
+
+def _phiseg_merge(b, cfg, post_z, cat):
+    """Top-down merge and per-level heads of likelihoods.phiseg (likelihoods.py:204-221)."""
+    nc, Lv, R = cfg.nc, cfg.L, cfg.R
+    d = R - Lv
+    if d == 0:
+        raise NotImplementedError('resolution_levels == latent_levels')
+    post_c = [None] * Lv
     post_c[Lv - 1] = post_z[Lv - 1]
     for i in reversed(range(Lv - 1)):
         u = b.up(post_c[i + 1])
-        if d == 0:      # no pre-upsampling: the concat buffer was not created above
-            cat[i] = Buf(pr, B, u.H, u.W, 2 * nc[i], b.adt)
-            pr.emit('phs_copy_cast', post_z[i].desc(), cat[i].act(0, nc[i]).desc())
-            raise NotImplementedError('resolution_levels == latent_levels')
         b.conv(u, 'likelihood/post_z%d_ups_c' % (i + 1), 3, nc[i], out=cat[i].act(nc[i], nc[i]))
         h = b.conv(cat[i].act(), 'likelihood/post_c_%d_1' % i, 3, nc[i + d])
         post_c[i] = b.conv(h, 'likelihood/post_c_%d_2' % i, 3, nc[i + d])
     return [b.conv(post_c[i], 'likelihood/y_lvl%d' % i, 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32)
             for i in range(Lv)]
+
+
+def _phiseg_likelihood(b, cfg, z):
+    """likelihoods.phiseg (likelihoods.py:162-223) on given latents.  Returns native-resolution head outputs (the
+    nearest-neighbour resize of :221 is folded into the loss / aggregation kernels).  The per-level towers only depend
+    on their own z: the coarse levels (small, latency-bound launches) run on a side lane."""
+    Lv = cfg.L
+    post_z, cat = [None] * Lv, [None] * Lv
+    towers = Lv > 2
+    if towers:
+        b.fork([1])
+    for i in range(Lv):
+        b.set_lane(1 if (towers and i >= 2) else 0)
+        post_z[i] = _phiseg_tower(b, cfg, i, z[i], cat)
+    if towers:
+        b.join([1])
+    b.set_lane(0)
+    return _phiseg_merge(b, cfg, post_z, cat)
 
 
 def _probunet_likelihood(b, cfg, z, x):
