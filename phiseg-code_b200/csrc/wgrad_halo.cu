@@ -39,7 +39,8 @@ struct WgradHaloParams {
   int slabw;       // channels per X box: 64 (128B swizzle) or 32 (64B swizzle)
   int a_boxes;     // X boxes per stage (2 or 4 channel slabs, or 1 when kw shifts are stacked along M)
   int a_lbo;       // bytes between the M slabs as the MMA sees them
-  int n_acc;       // accumulators = kw groups
+  int nkh;         // filter rows per CTA: 1 (kh from the work item) or 3 (18-row halo tile, narrow inputs)
+  int n_acc;       // accumulators = kw groups (per filter row)
   int kw_step;     // kw distance between accumulators
   int kw_per_acc;  // kw shifts stacked in one accumulator (1, 2 or 4)
   int nb;          // output channels per CTA (N of the MMA)
@@ -58,8 +59,11 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rowA = p.slabw * 2, rowB = p.slabB * 2;
-  const uint32_t boxA_bytes = BR_H * HALO_W * rowA, boxB_bytes = BR_H * BR_W * rowB;
-  const uint32_t A_BYTES = boxA_bytes * p.a_boxes, B_BYTES = boxB_bytes * p.nslabB;
+  const int halo_h = p.nkh == 3 ? BR_H + 2 : BR_H;
+  const uint32_t boxA_bytes = halo_h * HALO_W * rowA, boxB_bytes = BR_H * BR_W * rowB;
+  // every TMA box starts on a 1024-byte boundary (swizzle pattern anchor); TX bytes are the boxes' own sizes
+  const uint32_t A_BYTES = (boxA_bytes * p.a_boxes + 1023u) & ~1023u, B_BYTES = boxB_bytes * p.nslabB;
+  const uint32_t TX_BYTES = boxA_bytes * p.a_boxes + B_BYTES;
   const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = smem_u32(bars);
@@ -69,8 +73,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   // work item: kh fastest so the three CTAs sharing the same bricks run together
   int item = blockIdx.x;
-  const int kh = item % 3;
-  item /= 3;
+  const int kh = p.nkh == 3 ? 0 : item % 3;
+  if (p.nkh != 3) item /= 3;
   const int cib = item % p.ci_blocks;
   const int cob = item / p.ci_blocks;
   const int t_begin = blockIdx.y * p.bricks_per_split;
@@ -93,7 +97,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = tmem_base_s;
 
   // lean, warp-uniform issue loops (see conv_halo.cu): counters instead of divisions, descriptors advanced by adds
-  const int stages = p.stages, a_boxes = p.a_boxes, nslabB = p.nslabB, n_acc = p.n_acc, nb = p.nb;
+  const int stages = p.stages, a_boxes = p.a_boxes, nslabB = p.nslabB, n_acc = p.n_acc, nb = p.nb, nkh = p.nkh;
   if (warp == 0) {
     int s = 0;
     uint32_t ph = 0;
@@ -106,10 +110,10 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int w0 = (r - bh * p.bricksW) * BR_W, h0 = bh * BR_H;
       mbar_wait(empty_bar(s), ph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        mbar_expect_tx(full_bar(s), TX_BYTES);
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
         for (int j = 0; j < a_boxes; ++j)
-          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), c_a + j * p.slabw, w0 - 1, h0 + kh - 1, n);
+          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), c_a + j * p.slabw, w0 - 1, h0 + (nkh == 3 ? 0 : kh) - 1, n);
         for (int j = 0; j < nslabB; ++j)
           tma_load_4d(a_s + A_BYTES + j * boxB_bytes, &tmDY, full_bar(s), c_b + j * p.slabB, w0, h0, n);
       }
@@ -134,13 +138,16 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
-        uint32_t a_lo = desc_lo(a_s, p.a_lbo);
+        uint32_t a_row = desc_lo(a_s, p.a_lbo);
         const uint32_t b_lo = desc_lo(a_s + A_BYTES, boxB_bytes);
         uint32_t d = tmem_base;
-        for (int g = 0; g < n_acc; ++g, a_lo += a_gstep, d += nb) {
+        for (int khi = 0; khi < nkh; ++khi, a_row += (HALO_W * rowA) >> 4) {   // filter row = halo rows khi..khi+15
+          uint32_t a_lo = a_row;
+          for (int g = 0; g < n_acc; ++g, a_lo += a_gstep, d += nb) {
 #pragma unroll
-          for (int k = 0; k < BR_H / 2; ++k)
-            umma_bf16_lohi(d, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, k ? 1u : first);
+            for (int k = 0; k < BR_H / 2; ++k)
+              umma_bf16_lohi(d, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, k ? 1u : first);
+          }
         }
         umma_commit(empty_bar(s));
         if (t == t_end - 1) umma_commit(tfull_bar);
@@ -155,7 +162,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int m = q * 32 + lane;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
-    for (int g = 0; g < p.n_acc; ++g) {
+    for (int ga = 0; ga < p.nkh * p.n_acc; ++ga) {
+      const int g = ga % p.n_acc;
+      const int khe = p.nkh == 3 ? ga / p.n_acc : kh;
       int kw, ci;
       if (p.kw_per_acc == 1) {
         kw = g;
@@ -165,8 +174,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         ci = m % p.slabw;
       }
       const bool valid = kw < 3 && ci < p.Cin;
-      float* dst = p.dw + ((size_t)((kh * 3 + (valid ? kw : 0)) * p.Cin + (valid ? ci : 0))) * p.Cout + cob * p.nb;
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + g * p.nb;
+      float* dst = p.dw + ((size_t)((khe * 3 + (valid ? kw : 0)) * p.Cin + (valid ? ci : 0))) * p.Cout + cob * p.nb;
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + ga * p.nb;
       for (int c0 = 0; c0 < p.nb; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(t0 + c0, r);
@@ -219,30 +228,35 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
     p.n_acc = 3;
     p.ci_blocks = (x->C + 127) / 128;
   }
-  // output-channel block: n_acc * nb TMEM columns <= 512, nb <= 128 keeps the stage small
-  p.co_blocks = (dy->C + 127) / 128;
+  // narrow inputs (kw shifts stacked along M): one CTA takes all three filter rows from an 18-row halo tile, so X and
+  // dY are read once instead of three times; wide inputs keep one filter row per CTA (N would drop to 32 otherwise)
+  p.nkh = p.kw_per_acc == 4 ? 3 : 1;   // measured: pays for 32-channel inputs only (64: N would shrink to 64)
+  // output-channel block: nkh * n_acc * nb TMEM columns <= 512, nb <= 128 keeps the stage small
+  const int max_nb = 512 / (p.nkh * p.n_acc) >= 128 ? 128 : (512 / (p.nkh * p.n_acc)) / 32 * 32;
+  p.co_blocks = (dy->C + max_nb - 1) / max_nb;
   p.nb = dy->C / p.co_blocks;
-  if (p.nb % 32) {
+  if (p.nb % 32 || p.nb > max_nb) {
     p.co_blocks = dy->C / 32;
     p.nb = 32;
   }
   p.slabB = p.nb % 64 == 0 ? 64 : 32;
   p.nslabB = p.nb / p.slabB;
-  int cols = p.n_acc * p.nb;
+  int cols = p.nkh * p.n_acc * p.nb;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   p.dw = dw;
-  const int stage_bytes = BR_H * HALO_W * p.slabw * 2 * p.a_boxes + BR_H * BR_W * p.nb * 2;
+  const int halo_h = p.nkh == 3 ? BR_H + 2 : BR_H;
+  const int stage_bytes = (halo_h * HALO_W * p.slabw * 2 * p.a_boxes + 1023) / 1024 * 1024 + BR_H * BR_W * p.nb * 2;
   int stages = (SMEM_OPTIN - 2048) / stage_bytes;
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
   p.stages = stages;
-  const int items = 3 * p.ci_blocks * p.co_blocks;
+  const int items = (p.nkh == 3 ? 1 : 3) * p.ci_blocks * p.co_blocks;
   int splits = (2 * num_sms() + items - 1) / items;
   if (splits > p.num_bricks) splits = p.num_bricks;
   if (splits < 1) splits = 1;
   p.bricks_per_split = (p.num_bricks + splits - 1) / splits;
   splits = (p.num_bricks + p.bricks_per_split - 1) / p.bricks_per_split;
   CUtensorMap tmX, tmDY;
-  int rc = activation_map(x, p.slabw, HALO_W, BR_H, 1, &tmX);
+  int rc = activation_map(x, p.slabw, HALO_W, halo_h, 1, &tmX);
   if (rc) return rc;
   rc = activation_map(dy, p.slabB, BR_W, BR_H, 1, &tmDY);
   if (rc) return rc;
