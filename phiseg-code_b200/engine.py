@@ -765,7 +765,17 @@ def build_program(cfg, params, B, kind, device):
             spre = {n: [None] for n, _ in nets}
             sig = {n: [None] for n, _ in nets}
             mu_out = {n: [None] for n, _ in nets}
-            for net, inp in nets:
+            unet = None
+            if need_lik and b.use_lanes:
+                b.fork([2])
+                b.set_lane(2)
+                unet = _probunet_unet(b, cfg, sp.x)
+                b.set_lane(0)
+            two = len(nets) == 2
+            if two:
+                b.fork([1])
+            for li, (net, inp) in enumerate(nets):
+                b.set_lane(li if two else 0)
                 h = inp
                 for r in range(R):
                     if r > 0:
@@ -776,6 +786,9 @@ def build_program(cfg, params, B, kind, device):
                 spre[net][0] = b.conv(h, '%s/pre_sigma' % net, 1, zd, normed=False, out_dtype=f32)
                 sig[net][0] = b.new(B, 1, 1, zd, f32)
                 mu_out[net][0] = b.new(B, 1, 1, zd, f32)
+            if two:
+                b.join([1])
+            b.set_lane(0)
             z = b.new(B, 1, 1, zd, f32)
             hw = (H >> (R - 1)) * (W >> (R - 1))
             _emit_latent(b, sp, 0, hw, mu, spre, sig, z, gen_mode, need_post, need_prior, gap=1, mu_out=mu_out)
@@ -784,9 +797,12 @@ def build_program(cfg, params, B, kind, device):
                 sp.mu, sp.sigma = mu_out['posterior'], sig['posterior']
             if need_prior:
                 sp.prior_mu, sp.prior_sigma = mu_out['prior'], sig['prior']
+            if unet is not None:
+                b.join([2])
+                sp.logits = _probunet_head(b, cfg, sp.z[0], *unet)
         else:
             sp.z = [b.new(B, 1, 1, zd, f32)]
-        if need_lik:
+        if need_lik and not (nets and b.use_lanes):
             sp.logits = _probunet_likelihood(b, cfg, sp.z[0], sp.x)
 
     # --- heads of the graph
@@ -902,6 +918,13 @@ def _phiseg_likelihood(b, cfg, z):
 
 def _probunet_likelihood(b, cfg, z, x):
     """likelihoods.prob_unet2D (likelihoods.py:81-159)."""
+    rc, hC = _probunet_unet(b, cfg, x)
+    return _probunet_head(b, cfg, z, rc, hC)
+
+
+def _probunet_unet(b, cfg, x):
+    """The U-Net of likelihoods.prob_unet2D up to the point where z is tiled in (likelihoods.py:104-146): it does not
+    depend on z, so it can run on its own lane next to the posterior / prior encoders."""
     nc, R, zd = cfg.nc, cfg.R, cfg.zdim0
     pr = b.prog
     B, H, W = b.B, cfg.H, cfg.W
@@ -932,7 +955,14 @@ def _probunet_likelihood(b, cfg, z, x):
                 rc = Buf(pr, B, H, W, nc[ii] + zd, b.adt)
                 out = rc.act(0, nc[ii])
             h = b.conv(h, 'likelihood/decoder/conv_%d_%d' % (jj, t), 3, nc[ii], out=out)
-    zs = rc.act(h.C, zd)
+    return rc, h.C
+
+
+def _probunet_head(b, cfg, z, rc, hC):
+    """z broadcast + the three 1x1 recombination convs + prediction head (likelihoods.py:147-157)."""
+    nc, zd = cfg.nc, cfg.zdim0
+    pr = b.prog
+    zs = rc.act(hC, zd)
     pr.emit('phs_broadcast_z', z.ptr, zs.desc())          # tf.tile of z over H x W (likelihoods.py:147-151)
     if b.want_grad:
         def bwd():
