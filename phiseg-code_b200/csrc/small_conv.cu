@@ -246,6 +246,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- filter gradient of a 1x1 head (wide x, NS <= 8 output channels): dW[ci][co] = sum_p x[p][ci] * dy[p][co] -------
+// thread <-> (8-channel vector of x, pixel lane) and ALL output channels: the 16-byte x load is shared by NS FMAs x 8.
+template <typename TW, typename TS, int NS>
+__global__ void __launch_bounds__(256)
+    wgrad_head_kernel(const TW* __restrict__ x, int ldx, int Cw, const TS* __restrict__ dy, int lds, int Cs, int64_t M,
+                      int64_t pix_per_block, float* __restrict__ dw) {
+  extern __shared__ float red[];  // [nvec][NS][8]
+  const int nvec = Cw / 8;
+  const int PL = blockDim.x / nvec;
+  const int cv = threadIdx.x % nvec, lp = threadIdx.x / nvec;
+  for (int i = threadIdx.x; i < nvec * NS * 8; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[NS][8];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[s][o] = 0.f;
+  if (lp < PL) {
+    const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+    const int64_t p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
+    constexpr int U = 4;
+    for (int64_t p = p0 + lp; p < p1; p += (int64_t)U * PL) {
+      float v[U][8], d[U][NS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t q = p + (int64_t)u * PL;
+        if (q < p1) {
+          ldv<TW, 8>(x + q * ldx + cv * 8, v[u]);
+#pragma unroll
+          for (int s = 0; s < NS; ++s) d[u][s] = s < Cs ? ldf<TS>(dy + q * lds + s) : 0.f;
+        } else {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) v[u][o] = 0.f;
+#pragma unroll
+          for (int s = 0; s < NS; ++s) d[u][s] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[s][o] = fmaf(d[u][s], v[u][o], acc[s][o]);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int o = 0; o < 8; ++o) atomicAdd(&red[(cv * NS + s) * 8 + o], acc[s][o]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nvec * NS * 8; i += blockDim.x) {
+    const int o = i & 7, s2 = (i >> 3) % NS, c2 = (i >> 3) / NS;
+    if (s2 < Cs) atomicAdd(dw + (size_t)(c2 * 8 + o) * Cs + s2, red[i]);   // ksize 1: [ci][co]
+  }
+}
+
 }  // namespace
 
 // returns 1 if handled, 0 if the shape is not for these kernels, <0 / >0 on error
@@ -334,6 +390,34 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
   }
   const int wes = wd->dtype == PHS_BF16 ? 2 : 4;
   if (wd->ld % 8 != 0 || ((uintptr_t)wd->ptr % (8 * wes > 16 ? 16 : 8 * wes)) != 0) return 0;
+  if (!small_is_x && wd->C / 8 <= 32) {
+    // 1x1 head: one thread per (x vector, pixel lane) for all output channels
+    const int nvec = wd->C / 8;
+    int64_t splits = 148 * 4;
+    if (splits > (M + 255) / 256) splits = (M + 255) / 256;
+    if (splits < 1) splits = 1;
+    const int64_t ppb = (M + splits - 1) / splits;
+    splits = (M + ppb - 1) / ppb;
+    const int ns = s->C <= 2 ? 2 : s->C <= 4 ? 4 : 8;
+    const size_t smem = (size_t)nvec * ns * 8 * sizeof(float);
+#define LAUNCH_WH(TW, TS, NSV)                                                                                     \
+  wgrad_head_kernel<TW, TS, NSV><<<(unsigned)splits, 256, smem, st>>>((const TW*)wd->ptr, wd->ld, wd->C, (const TS*)s->ptr, \
+                                                                      s->ld, s->C, M, ppb, dw)
+#define LAUNCH_WH_N(TW, TS)              \
+  do {                                   \
+    if (ns == 2) LAUNCH_WH(TW, TS, 2);   \
+    else if (ns == 4) LAUNCH_WH(TW, TS, 4); \
+    else LAUNCH_WH(TW, TS, 8);           \
+  } while (0)
+    if (wd->dtype == PHS_F32 && s->dtype == PHS_F32) LAUNCH_WH_N(float, float);
+    else if (wd->dtype == PHS_F32) LAUNCH_WH_N(float, bf16);
+    else if (s->dtype == PHS_F32) LAUNCH_WH_N(bf16, float);
+    else LAUNCH_WH_N(bf16, bf16);
+#undef LAUNCH_WH_N
+#undef LAUNCH_WH
+    int rc = phs_check_launch("wgrad_head_kernel");
+    return rc ? rc : 1;
+  }
   const int taps = ksize * ksize;
   const int pairs = taps * s->C * (wd->C / 8);
   // PB pairs per block (32 or 64); the other 256 / PB thread groups are pixel lanes over the block's pixel range
