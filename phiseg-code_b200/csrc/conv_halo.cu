@@ -44,6 +44,8 @@ struct HaloParams {
   const float* bias;
   int accumulate;
   float* stats;               // [N][Cout][2] or null
+  int stage_g;                // 0: direct register -> global stores; 32 | 64: channels per smem-staged TMA store group
+  long long* trace;           // PHS_HALO_TRACE: per-role clock64 stamps of the first CTAs (tools/trace_halo.py)
   int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
 };
 
@@ -99,13 +101,21 @@ __device__ __forceinline__ float transpose_reduce16(const float* v, int lane) {
 
 template <int BK>
 __global__ void __launch_bounds__(192, 2)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * HB_MAX_A + 2 * HB_MAX_B + 4];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // optional timeline of the first 8 CTAs: trace[(cta * 3 + role) * 256 + k], role 0 producer / 1 MMA / 2 epilogue warp 2
+  long long* trc = (p.trace && blockIdx.x < 8 && lane == 0 && warp < 3) ? p.trace + (blockIdx.x * 3 + warp) * 256 : nullptr;
+  int tri = 0;
+  auto stamp = [&]() {
+    if (trc && tri < 256) trc[tri++] = clock64();
+  };
+  stamp();
   constexpr uint32_t ROW = BK * 2;
   const int HW_ = SUB_W * p.S + 2;                 // halo width in pixels
   const uint32_t a_bytes = (uint32_t)(TILE_H + 2) * HW_ * ROW;
@@ -123,6 +133,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.stage_g) tma_prefetch_desc(&tmY);
     for (int s = 0; s < p.na; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), 1);
@@ -143,6 +154,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  stamp();
 
   // contiguous tile range of this CTA
   const int t_begin = (int)((int64_t)p.num_tiles * blockIdx.x / gridDim.x);
@@ -174,6 +186,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         __syncwarp();
+        stamp();
         if (++sa == na) { sa = 0; pha ^= 1; }
         if (resident && tile != t_begin) continue;
 #pragma unroll 1
@@ -206,10 +219,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(tempty(acc), aph ^ 1);
       tc_fence_after();
+      stamp();
       const uint32_t d0 = tmem_base + acc * acc_cols;
       for (int kc = 0; kc < kchunks; ++kc) {
         mbar_wait(a_full(sa), pha);
         tc_fence_after();
+        if (kc == 0) stamp();
         const uint32_t a_base_lo = desc_lo(smem0 + sa * a_stage_bytes, 16);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -237,6 +252,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (++sa == na) { sa = 0; pha ^= 1; }
       }
+      stamp();
       if (++acc == acc_stages) { acc = 0; aph ^= 1; }
     }
   } else {
@@ -260,46 +276,129 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
       }
     };
-    for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
-      const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
-      const int n = tile / tiles_per_img;
-      const int r = tile - n * tiles_per_img;
-      const int h = (r / p.tilesW) * TILE_H + m / SUB_W;
-      const int wbase = (r % p.tilesW) * SUB_W * p.S + m % SUB_W;
-      if (n != st_n) {
-        flush();
-        st_n = n;
-      }
-      mbar_wait(tfull(acc), aph);
-      tc_fence_after();
-      for (int s = 0; s < p.S; ++s) {
-        const size_t pix = ((size_t)n * p.H + h) * p.W + wbase + s * SUB_W;
-        const uint32_t t0 = tmem_base + acc * p.acc_cols + s * p.Cout + ((uint32_t)(q * 32) << 16);
+    if (p.stage_g) {
+      // Outputs leave through shared memory and the TMA unit: a thread owns one pixel row of the sub-tile, so direct
+      // stores are 16-byte pieces 2*ld bytes apart (one L2 request each, ~0.45 requests/clk/SM: measured 7 B/clk/SM).
+      // Instead every thread writes its bf16 row into a 128-row x G-channel staging tile (the TMA swizzle keeps the
+      // 16-byte st.shared conflict-free), and one thread issues a cp.async.bulk.tensor store of the tile: full
+      // 64/128-byte rows, no LSU traffic.  Two staging tiles: the store of group g-1 drains while group g is written.
+      const uint32_t G = p.stage_g, rowb = 2 * G;
+      const uint32_t stage_bytes = 128 * rowb;
+      const uint32_t stage0 = smem_b0 + nb * b_bytes;
+      const uint32_t xr = G == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
+      const uint32_t my_row = m * rowb;
+      const bool issuer = threadIdx.x == 64;
+      uint32_t sg = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
+        const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
+        const int n = tile / tiles_per_img;
+        const int r = tile - n * tiles_per_img;
+        const int h0 = (r / p.tilesW) * TILE_H;
+        const int w0 = (r % p.tilesW) * SUB_W * p.S;
+        if (n != st_n) {
+          flush();
+          st_n = n;
+        }
+        mbar_wait(tfull(acc), aph);
+        tc_fence_after();
+        stamp();
+        for (int s = 0; s < p.S; ++s) {
+          const uint32_t t0 = tmem_base + acc * p.acc_cols + s * p.Cout + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (j * 16 < p.Cout) {
-            uint32_t rr[16];
-            tmem_ld16(t0 + j * 16, rr);
-            tmem_ld_wait();
-            float v[16];
+          for (int jj = 0; jj < 8; ++jj) {
+            if (jj * 32 < p.Cout) {
+              uint32_t rr[32];
+              tmem_ld32(t0 + jj * 32, rr);
+              tmem_ld_wait();
+              float v[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[j * 16 + i];
-            if (p.dbg & 4) {
-            } else if (p.y_f32) store16<float>((float*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
-            else store16<bf16>((bf16*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
-            if (p.stats) {
-              float sq[16];
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[jj * 32 + i];
+              const uint32_t dst = stage0 + (sg & 1) * stage_bytes + my_row;
+              const uint32_t slot0 = ((uint32_t)(jj * 32) & (G - 1)) >> 3;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-              st_s[j] += transpose_reduce16(v, lane);
-              st_q[j] += transpose_reduce16(sq, lane);
+              for (int t = 0; t < 4; ++t) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[t * 8 + 2 * i], v[t * 8 + 2 * i + 1]);
+                  w4[i] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                st_shared_v4(dst + (((slot0 + t) ^ xr) << 4), w4[0], w4[1], w4[2], w4[3]);
+              }
+              if ((((uint32_t)(jj + 1) * 32) & (G - 1)) == 0) {   // the group is complete: hand it to the TMA unit
+                fence_proxy_async();
+                if (issuer) bulk_wait_read<0>();                  // the other staging tile (group sg-1) has been read
+                __syncwarp();
+                named_bar_sync(1, 128);
+                if (issuer && !(p.dbg & 4)) {
+                  tma_store_4d(&tmY, stage0 + (sg & 1) * stage_bytes, (int)(((uint32_t)(jj * 32)) & ~(G - 1)), w0 + s * SUB_W, h0, n);
+                  bulk_commit();
+                }
+                ++sg;
+              }
+              if (p.stats) {
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                  float sq[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) sq[i] = v[hlf * 16 + i] * v[hlf * 16 + i];
+                  st_s[2 * jj + hlf] += transpose_reduce16(v + hlf * 16, lane);
+                  st_q[2 * jj + hlf] += transpose_reduce16(sq, lane);
+                }
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(acc));
+        stamp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));
+      if (issuer) bulk_wait<0>();
+    } else {
+      for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
+        const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
+        const int n = tile / tiles_per_img;
+        const int r = tile - n * tiles_per_img;
+        const int h = (r / p.tilesW) * TILE_H + m / SUB_W;
+        const int wbase = (r % p.tilesW) * SUB_W * p.S + m % SUB_W;
+        if (n != st_n) {
+          flush();
+          st_n = n;
+        }
+        mbar_wait(tfull(acc), aph);
+        tc_fence_after();
+        stamp();
+        for (int s = 0; s < p.S; ++s) {
+          const size_t pix = ((size_t)n * p.H + h) * p.W + wbase + s * SUB_W;
+          const uint32_t t0 = tmem_base + acc * p.acc_cols + s * p.Cout + ((uint32_t)(q * 32) << 16);
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j * 16 < p.Cout) {
+              uint32_t rr[16];
+              tmem_ld16(t0 + j * 16, rr);
+              tmem_ld_wait();
+              float v[16];
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[j * 16 + i];
+              if (p.dbg & 4) {
+              } else if (p.y_f32) store16<float>((float*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
+              else store16<bf16>((bf16*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
+              if (p.stats) {
+                float sq[16];
+  #pragma unroll
+                for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+                st_s[j] += transpose_reduce16(v, lane);
+                st_q[j] += transpose_reduce16(sq, lane);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(acc));
+        stamp();
+      }
     }
     flush();
   }
@@ -327,44 +426,88 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   p.kchunks = x->C / BK;
   const int subs_w = x->W / SUB_W;
   const int64_t total_subs = (int64_t)x->N * (x->H / TILE_H) * subs_w;
-  // Two CTAs per SM (each <= 256 TMEM columns, ~110 KB of shared memory): while one CTA drains its accumulators or
-  // waits on a barrier, the other one keeps the tensor pipe busy.  One accumulator set of S sub-tiles per CTA.
-  // S: as many sub-tiles as TMEM, the halo stage budget and the image width allow, leaving >= 2 super-tiles per SM.
-  const int budget = getenv("PHS_HALO_1CTA") ? SMEM_OPTIN - 2048 : 110 * 1024;
-  const int max_cols = 256;
-  int S = 1;
-  while (S * 2 * y->C <= max_cols && subs_w % (S * 2) == 0 &&
-         2 * ((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024 + 4 * y->C * ROW <= budget &&
-         total_subs / (S * 2) >= 2 * num_sms())
-    S *= 2;
-  p.S = S;
-  p.tilesW = subs_w / S;
-  p.tilesH = x->H / TILE_H;
-  p.num_tiles = p.tilesW * p.tilesH * x->N;
-  const int a_bytes = (TILE_H + 2) * (SUB_W * S + 2) * ROW;
-  p.a_stage_bytes = (a_bytes + 1023) / 1024 * 1024;
+  // Geometry.  The filter tiles are re-streamed from L2 for every super-tile, and L2 -> SM bandwidth (~42 B/clk per SM)
+  // is what bounds the wide layers: a [Cout][64] tile feeds only 4*S MMAs, so S (sub-tiles sharing one filter tile) has
+  // to be as large as TMEM allows.  Two regimes:
+  //   ctas == 2: two CTAs per SM (<= 256 TMEM columns, ~110 KB each) cover each other's epilogue / barrier latency;
+  //   ctas == 1: one CTA per SM with all 512 TMEM columns and ~220 KB: S up to 4 for 128 channels, a deep filter ring.
+  const char* e_ctas = getenv("PHS_HALO_CTAS");
+  const char* e_s = getenv("PHS_HALO_S");
+  const char* e_acc = getenv("PHS_HALO_ACC");
+  const char* e_g = getenv("PHS_HALO_G");
+  const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") ? 1 : 2);
+  // dynamic shared memory per CTA: 228 KB per SM, 1 KB reserved + ~1.8 KB static per CTA, 1 KB alignment slack
+  const int budget_all = ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896;
+  const int max_cols = ctas_per_sm == 1 ? 512 : 256;
+  const int min_tiles = ctas_per_sm * num_sms();
   const int b_bytes = y->C * ROW;
-  const int cols = S * y->C;
-  p.acc_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
-  // double-buffer the accumulators whenever the CTA's TMEM share allows it (the epilogue of tile i then overlaps the
-  // MMAs of tile i+1 inside the CTA as well)
-  const int tmem_share = getenv("PHS_HALO_1CTA") ? 512 : 256;
-  p.acc_stages = 2 * p.acc_cols <= tmem_share ? 2 : 1;
-  p.tmem_cols = p.acc_cols * p.acc_stages;
-  // filter resident?
-  const int b_all = p.kchunks * 9 * b_bytes;
-  if (p.kchunks * 9 <= HB_MAX_B && b_all + 2 * (int)p.a_stage_bytes <= budget) {
-    p.b_resident = 1;
-    p.nb = p.kchunks * 9;
-    p.na = (budget - b_all) / (int)p.a_stage_bytes;
-    if (p.na > HB_MAX_A) p.na = HB_MAX_A;
-  } else {
+  // staged TMA-store epilogue: bf16 outputs that are not accumulated onto, 32-channel granularity
+  const bool can_stage = !accumulate && y->dtype == PHS_BF16 && y->C % 32 == 0 && y->ld % 8 == 0 && aligned16(y->ptr) &&
+                         !(e_g && atoi(e_g) == 0);
+  auto geometry = [&](int G) -> bool {
+    const int budget = budget_all - (G ? 2 * 128 * 2 * G : 0);
+    int S = 1;
+    if (e_s) {
+      S = atoi(e_s);
+      while (S > 1 && (S * y->C > max_cols || subs_w % S != 0)) S /= 2;
+    } else {
+      while (S * 2 * y->C <= max_cols && subs_w % (S * 2) == 0 &&
+             2 * ((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024 + 4 * b_bytes <= budget &&
+             total_subs / (S * 2) >= min_tiles)
+        S *= 2;
+    }
+    p.S = S;
+    p.stage_g = G;
+    p.tilesW = subs_w / S;
+    p.tilesH = x->H / TILE_H;
+    p.num_tiles = p.tilesW * p.tilesH * x->N;
+    const int a_bytes = (TILE_H + 2) * (SUB_W * S + 2) * ROW;
+    p.a_stage_bytes = (a_bytes + 1023) / 1024 * 1024;
+    const int cols = S * y->C;
+    p.acc_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    // double-buffer the accumulators whenever the CTA's TMEM share allows it (the epilogue of tile i then overlaps
+    // the MMAs of tile i+1 inside the CTA as well)
+    p.acc_stages = 2 * p.acc_cols <= max_cols ? 2 : 1;
+    if (e_acc && atoi(e_acc) == 1) p.acc_stages = 1;
+    p.tmem_cols = p.acc_cols * p.acc_stages;
+    // filter resident?
+    const int b_all = p.kchunks * 9 * b_bytes;
+    if (p.kchunks * 9 <= HB_MAX_B && b_all + 2 * (int)p.a_stage_bytes <= budget) {
+      p.b_resident = 1;
+      p.nb = p.kchunks * 9;
+      p.na = (budget - b_all) / (int)p.a_stage_bytes;
+      if (p.na > HB_MAX_A) p.na = HB_MAX_A;
+      return true;
+    }
     p.b_resident = 0;
     p.na = 2;
     p.nb = (budget - 2 * (int)p.a_stage_bytes) / b_bytes;
     if (p.nb > 12) p.nb = 12;
-    if (p.nb < 2) return -3;   // caller falls back to the shifted-box kernel
+    return p.nb >= 2;
+  };
+  // The staging tiles come out of the filter ring.  A [Cout][64] filter stage feeds S*4 MMAs (~max(32, Cout/2) clk each)
+  // and a ring refill is a ~2000 clk round trip, so narrow-output layers need a deep ring more than they need fast
+  // stores: staging is dropped when it would leave the ring both short of that and less than half as deep as without it.
+  int s_plain = 1;
+  auto ring_ok = [&](int nb_plain) {
+    if (p.S < s_plain) return false;   // never trade filter-tile reuse for staging
+    if (p.b_resident) return true;
+    const int per_stage = p.S * 4 * (y->C / 2 > 32 ? y->C / 2 : 32);
+    const int need = (2000 + per_stage - 1) / per_stage;
+    return p.nb >= need || 2 * p.nb > nb_plain;
+  };
+  bool ok = false;
+  if (can_stage) {
+    int nb_plain = geometry(0) ? (p.b_resident ? 1 << 20 : p.nb) : 0;
+    s_plain = p.S;
+    int G = e_g ? atoi(e_g) : 64;
+    if (G != 32 && (G != 64 || y->C % 64 != 0)) G = 32;
+    ok = geometry(G) && (p.b_resident || p.nb >= 3 || G == 32) && ring_ok(nb_plain);
+    if (!ok && G == 64) ok = geometry(32) && ring_ok(nb_plain);
+    if (e_g && atoi(e_g) != 0 && !ok) ok = geometry(atoi(e_g) == 64 && y->C % 64 == 0 ? 64 : 32);
   }
+  if (!ok) ok = geometry(0);
+  if (!ok) return -3;   // caller falls back to the shifted-box kernel
   p.y = y->ptr; p.y_ld = y->ld; p.y_f32 = y->dtype == PHS_F32;
   p.bias = bias;
   p.accumulate = accumulate;
@@ -372,24 +515,28 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   {
     const char* e = getenv("PHS_HALO_DBG");
     p.dbg = e ? atoi(e) : 0;
+    const char* t = getenv("PHS_HALO_TRACE");
+    p.trace = t ? (long long*)strtoull(t, nullptr, 0) : nullptr;
   }
   CUtensorMap tmA, tmB;
-  int rc = activation_map(x, BK, SUB_W * S + 2, TILE_H + 2, 1, &tmA);
+  int rc = activation_map(x, BK, SUB_W * p.S + 2, TILE_H + 2, 1, &tmA);
   if (rc) return rc;
   rc = filter_map(w, 9 * x->C, y->C, BK, &tmB);
   if (rc) return rc;
-  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + 1024;
-  const int ctas = (getenv("PHS_HALO_1CTA") ? 1 : 2) * num_sms();
+  CUtensorMap tmY = tmA;
+  if (p.stage_g && (rc = activation_map(y, p.stage_g, SUB_W, TILE_H, 1, &tmY))) return rc;
+  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0) + 1024;
+  const int ctas = ctas_per_sm * num_sms();
   const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<64>, &attr))) return rc;
-    conv_halo_kernel<64><<<grid, 192, smem, st>>>(tmA, tmB, p);
+    conv_halo_kernel<64><<<grid, 192, smem, st>>>(tmA, tmB, tmY, p);
   } else {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<32>, &attr))) return rc;
-    conv_halo_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, p);
+    conv_halo_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, tmY, p);
   }
   return phs_check_launch("conv_halo_kernel");
 }
