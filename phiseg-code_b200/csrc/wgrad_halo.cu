@@ -21,6 +21,7 @@
 //
 // A CTA owns (kh, ci block, co block, a slice of the bricks); partial sums go to the fp32 HWIO gradient with
 // red.global.add.v4.f32.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_host.cuh"
@@ -62,7 +63,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int halo_h = p.nkh == 3 ? BR_H + 2 : BR_H;
   const uint32_t boxA_bytes = halo_h * HALO_W * rowA, boxB_bytes = BR_H * BR_W * rowB;
   // every TMA box starts on a 1024-byte boundary (swizzle pattern anchor); TX bytes are the boxes' own sizes
-  const uint32_t A_BYTES = (boxA_bytes * p.a_boxes + 1023u) & ~1023u, B_BYTES = boxB_bytes * p.nslabB;
+  const uint32_t boxA_stride = (boxA_bytes + 1023u) & ~1023u;
+  const uint32_t A_BYTES = boxA_stride * p.a_boxes, B_BYTES = boxB_bytes * p.nslabB;
   const uint32_t TX_BYTES = boxA_bytes * p.a_boxes + B_BYTES;
   const uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -113,7 +115,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_expect_tx(full_bar(s), TX_BYTES);
         const uint32_t a_s = smem0 + s * STAGE_BYTES;
         for (int j = 0; j < a_boxes; ++j)
-          tma_load_4d(a_s + j * boxA_bytes, &tmX, full_bar(s), c_a + j * p.slabw, w0 - 1, h0 + (nkh == 3 ? 0 : kh) - 1, n);
+          tma_load_4d(a_s + j * boxA_stride, &tmX, full_bar(s), c_a + j * p.slabw, w0 - 1, h0 + (nkh == 3 ? 0 : kh) - 1, n);
         for (int j = 0; j < nslabB; ++j)
           tma_load_4d(a_s + A_BYTES + j * boxB_bytes, &tmDY, full_bar(s), c_b + j * p.slabB, w0, h0, n);
       }
@@ -222,7 +224,7 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   } else {
     p.slabw = x->C % 64 == 0 ? 64 : 32;
     p.a_boxes = 128 / p.slabw;
-    p.a_lbo = BR_H * HALO_W * p.slabw * 2;
+    p.a_lbo = 0;                   // set below: the (1024-aligned) stride between the channel-slab boxes
     p.kw_per_acc = 1;
     p.kw_step = 1;
     p.n_acc = 3;
@@ -230,7 +232,13 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   }
   // narrow inputs (kw shifts stacked along M): one CTA takes all three filter rows from an 18-row halo tile, so X and
   // dY are read once instead of three times; wide inputs keep one filter row per CTA (N would drop to 32 otherwise)
-  p.nkh = p.kw_per_acc == 4 ? 3 : 1;   // measured: pays for 32-channel inputs only (64: N would shrink to 64)
+  // (measured for 64-channel inputs: does not pay, N would shrink to 64).  Wide inputs with 32 output channels are the
+  // other case where it fits (9 accumulators of 32 columns): X, the big operand, is then read once instead of three times.
+  p.nkh = p.kw_per_acc == 4 ? 3 : 1;
+  {
+    const char* e = getenv("PHS_WGRAD_NKH3");
+    if (p.kw_per_acc == 1 && dy->C == 32 && !(e && atoi(e) == 0)) p.nkh = 3;
+  }
   // output-channel block: nkh * n_acc * nb TMEM columns <= 512, nb <= 128 keeps the stage small
   const int max_nb = 512 / (p.nkh * p.n_acc) >= 128 ? 128 : (512 / (p.nkh * p.n_acc)) / 32 * 32;
   p.co_blocks = (dy->C + max_nb - 1) / max_nb;
@@ -245,7 +253,9 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   p.dw = dw;
   const int halo_h = p.nkh == 3 ? BR_H + 2 : BR_H;
-  const int stage_bytes = (halo_h * HALO_W * p.slabw * 2 * p.a_boxes + 1023) / 1024 * 1024 + BR_H * BR_W * p.nb * 2;
+  const int box_stride = (halo_h * HALO_W * p.slabw * 2 + 1023) / 1024 * 1024;
+  if (p.kw_per_acc == 1) p.a_lbo = box_stride;
+  const int stage_bytes = box_stride * p.a_boxes + BR_H * BR_W * p.nb * 2;
   int stages = (SMEM_OPTIN - 2048) / stage_bytes;
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
   p.stages = stages;

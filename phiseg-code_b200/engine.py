@@ -380,6 +380,12 @@ class Program:
         st.lane = 0
         self.steps.append(st)
 
+    def emit_after(self, src, dst):
+        """Lane dst waits for everything enqueued so far on lane src (a one-way dependency, no region)."""
+        st = Step((None, ((src, dst),), 'after'))
+        st.lane = 0
+        self.steps.append(st)
+
     def vec(self, n, zero=False):
         t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=self.device)
         self.keep.append(t)
@@ -395,6 +401,14 @@ class Program:
         streams = {0: main}
         for step in (self.steps if steps is None else steps):
             fn, args, name = step
+            if fn is None and name == 'after':
+                src, dst = args[0]
+                if dst not in streams:
+                    streams[dst] = self._side_stream(dst)
+                ev = torch.cuda.Event()
+                ev.record(streams[src])
+                streams[dst].wait_event(ev)
+                continue
             if fn is None:
                 for ln in args[0]:
                     if ln not in streams:
@@ -441,6 +455,10 @@ class Builder:
         self.n_conv_flop = 0
         self.lane = 0
         self.use_lanes = os.environ.get('PHS_NO_LANES') is None
+        # filter gradients hang off the backward chain (nothing but the optimizer consumes them): they go to their own
+        # lane so the tensor-bound wgrad kernels overlap the HBM-bound normalisation adjoints of the layers below
+        self.wlane = 3 if (self.use_lanes and os.environ.get('PHS_NO_WLANE') is None) else None
+        self.wlane_used = False
 
     # -- helpers ------------------------------------------------------------------------------------------
     def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
@@ -557,12 +575,18 @@ class Builder:
                 else:
                     dy = ga
                     db = P.ptr(scope + '/b', 'g') if bias is not None else None
+                lane = self.lane
+                if self.wlane is not None:
+                    pr.emit_after(lane, self.wlane)
+                    self.lane = self.wlane
+                    self.wlane_used = True
                 if pad_in:
                     scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
                     self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
                     self.emit('phs_axpy_f32', P.ptr(wname, 'g'), scratch.data_ptr(), 9 * cin_real * cout, 1.0)
                 else:
                     self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
+                self.lane = lane
                 if need_dx:
                     gx = x.grad()
                     acc = int(x.grad_written())
@@ -621,6 +645,8 @@ class Builder:
             self.lane = getattr(f, 'lane', 0)
             f()
         self.lane = 0
+        if self.wlane_used:
+            self.prog.emit_sync('join', [self.wlane])
         self.tape = []
 
 

@@ -47,6 +47,9 @@ TC_CASES = [  # N, H, W, Cin, Cout, k
     (2, 16, 16, 96, 32, 1),      # 1x1
     (1, 24, 40, 64, 96, 3),      # sizes that are not powers of two: bricks overhang the image
     (1, 256, 256, 32, 32, 3),    # two bricks per image row
+    (2, 32, 32, 192, 32, 3),     # wide input, 32 outputs: wgrad takes all three filter rows per CTA (two channel-slab boxes)
+    (2, 32, 32, 32, 192, 3),     # BK=32 activations, 192 outputs: three 64-channel TMA-store groups per sub-tile
+    (2, 16, 64, 128, 32, 3),
 ]
 
 
