@@ -21,6 +21,35 @@ int phs_check_launch(const char* what);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Division of a 31-bit index by a launch-time constant as multiply-high + shift (a 64-bit `/` or `%` costs ~50-100
+// instructions, enough to make a 16-byte-per-thread streaming kernel ALU bound).  Valid for n < 2^31.
+struct fdiv_t { uint32_t d, m, s; };
+static inline fdiv_t fdiv_make(uint32_t d) {
+  fdiv_t f;
+  f.d = d;
+  f.s = 0;
+  while ((1u << f.s) < d) ++f.s;
+  f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.s) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const fdiv_t& f) { return (__umulhi(n, f.m) + n) >> f.s; }
+// flat index -> (vector, w, h, n) of an [N][H][W][nvec] iteration space
+struct idx4_t { fdiv_t nvec, W, H; };
+static inline idx4_t idx4_make(int nvec, int W, int H) {
+  idx4_t r;
+  r.nvec = fdiv_make((uint32_t)nvec); r.W = fdiv_make((uint32_t)W); r.H = fdiv_make((uint32_t)H);
+  return r;
+}
+__device__ __forceinline__ void idx4_decode(uint32_t i, const idx4_t& f, int& cv, int& w, int& h, int& n) {
+  const uint32_t pix = fdiv(i, f.nvec);
+  cv = (int)(i - pix * f.nvec.d);
+  const uint32_t row = fdiv(pix, f.W);
+  w = (int)(pix - row * f.W.d);
+  const uint32_t img = fdiv(row, f.H);
+  h = (int)(row - img * f.H.d);
+  n = (int)img;
+}
+
 // ---- dtype-generic scalar/vector access ------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float ldf(const T* p);

@@ -508,20 +508,24 @@ int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* me
 }
 
 // ---- 2x2 average pool ------------------------------------------------------------------------------------
+// All the resampling kernels below are one 16-byte vector per thread; their index arithmetic is multiply-high
+// (idx4_decode) because 64-bit divisions made them ALU bound at ~2 TB/s.
+static int stream_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-    avgpool2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Ho, int Wo, int C,
-                        int64_t total) {
-  const int nvec = C / V;
+    avgpool2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Ho, int Wo, idx4_t ix,
+                        uint32_t total) {
   const int Wi = Wo * 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int wo = (int)(pix % Wo);
-    int64_t t = pix / Wo;
-    int ho = (int)(t % Ho);
-    int64_t n = t / Ho;
-    const T* p = x + ((n * (2 * Ho) + 2 * ho) * Wi + 2 * wo) * (int64_t)ldx + cv * V;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cv, wo, ho, n;
+    idx4_decode(i, ix, cv, wo, ho, n);
+    const T* p = x + (((int64_t)n * (2 * Ho) + 2 * ho) * Wi + 2 * wo) * (int64_t)ldx + cv * V;
     float a[V], b[V], c[V], d[V], o[V];
     ldv<T, V>(p, a);
     ldv<T, V>(p + ldx, b);
@@ -529,43 +533,39 @@ __global__ void __launch_bounds__(256)
     ldv<T, V>(p + (int64_t)Wi * ldx + ldx, d);
 #pragma unroll
     for (int k = 0; k < V; ++k) o[k] = 0.25f * ((a[k] + b[k]) + (c[k] + d[k]));
-    stv<T, V>(y + pix * ldy + cv * V, o);
+    stv<T, V>(y + (((int64_t)n * Ho + ho) * Wo + wo) * (int64_t)ldy + cv * V, o);
   }
 }
 
+// one thread per pooled pixel: its gradient goes to the 2x2 input block
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-    avgpool2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, int C,
-                        int64_t total, int accumulate) {
-  const int nvec = C / V;
-  const int Wo = Wi / 2, Ho = Hi / 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int w = (int)(pix % Wi);
-    int64_t t = pix / Wi;
-    int h = (int)(t % Hi);
-    int64_t n = t / Hi;
-    float g[V], o[V];
-    ldv<T, V>(dy + ((n * Ho + h / 2) * Wo + w / 2) * (int64_t)lddy + cv * V, g);
-    T* q = dx + pix * lddx + cv * V;
-    if (accumulate) {
-      ldv<T, V>(q, o);
+    avgpool2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Ho, int Wo, idx4_t ix,
+                        uint32_t total, int accumulate) {
+  const int Wi = Wo * 2;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cv, wo, ho, n;
+    idx4_decode(i, ix, cv, wo, ho, n);
+    float g[V];
+    ldv<T, V>(dy + (((int64_t)n * Ho + ho) * Wo + wo) * (int64_t)lddy + cv * V, g);
 #pragma unroll
-      for (int k = 0; k < V; ++k) o[k] += 0.25f * g[k];
-    } else {
+    for (int k = 0; k < V; ++k) g[k] *= 0.25f;
+    T* q = dx + (((int64_t)n * (2 * Ho) + 2 * ho) * Wi + 2 * wo) * (int64_t)lddx + cv * V;
 #pragma unroll
-      for (int k = 0; k < V; ++k) o[k] = 0.25f * g[k];
+    for (int r = 0; r < 4; ++r) {
+      T* qq = q + ((r >> 1) * (int64_t)Wi + (r & 1)) * lddx;
+      float o[V];
+      if (accumulate) {
+        ldv<T, V>(qq, o);
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] += g[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = g[k];
+      }
+      stv<T, V>(qq, o);
     }
-    stv<T, V>(q, o);
   }
-}
-
-static int stream_blocks(int64_t total) {
-  int64_t b = (total + 255) / 256;
-  if (b > 148 * 16) b = 148 * 16;
-  if (b < 1) b = 1;
-  return (int)b;
 }
 
 int phs_avgpool2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
@@ -574,9 +574,11 @@ int phs_avgpool2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
               "phs_avgpool2_fwd: shape mismatch (%d,%d,%d)->(%d,%d,%d)", x->H, x->W, x->C, y->H, y->W, y->C);
   int v = min_vec(pick_vec(x), pick_vec(y));
   int64_t total = (int64_t)y->N * y->H * y->W * (y->C / v);
+  PHS_REQUIRE(total < (1ll << 31), "phs_avgpool2_fwd: tensor too large");
+  const idx4_t ix = idx4_make(y->C / v, y->W, y->H);
   PHS_DISPATCH_DTYPE(x->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (avgpool2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, y->H, y->W, y->C, total))));
+                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, y->H, y->W, ix, (uint32_t)total))));
   return phs_check_launch("avgpool2_fwd");
 }
 
@@ -585,66 +587,62 @@ int phs_avgpool2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate,
   PHS_REQUIRE(dx->dtype == dy->dtype && dx->N == dy->N && dx->C == dy->C && dx->H == 2 * dy->H && dx->W == 2 * dy->W,
               "phs_avgpool2_bwd: shape mismatch");
   int v = min_vec(pick_vec(dx), pick_vec(dy));
-  int64_t total = (int64_t)dx->N * dx->H * dx->W * (dx->C / v);
+  int64_t total = (int64_t)dy->N * dy->H * dy->W * (dy->C / v);
+  PHS_REQUIRE(total < (1ll << 31), "phs_avgpool2_bwd: tensor too large");
+  const idx4_t ix = idx4_make(dy->C / v, dy->W, dy->H);
   PHS_DISPATCH_DTYPE(dx->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (avgpool2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, dx->C, total,
+                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dy->H, dy->W, ix, (uint32_t)total,
                                                 accumulate))));
   return phs_check_launch("avgpool2_bwd");
 }
 
 // ---- TF1 legacy bilinear x2 ------------------------------------------------------------------------------
-// forward: out[2k] = in[k]; out[2k+1] = 0.5*(in[k] + in[min(k+1,n-1)]) per axis
+// forward: out[2k] = in[k]; out[2k+1] = 0.5*(in[k] + in[min(k+1,n-1)]) per axis.  One thread per INPUT pixel vector:
+// four loads (the pixel, its right / lower / diagonal neighbours) make the 2x2 output block.
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-    upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Hi, int Wi, int C,
-                         int64_t total) {
-  const int nvec = C / V;
-  const int Ho = 2 * Hi, Wo = 2 * Wi;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int wo = (int)(pix % Wo);
-    int64_t t = pix / Wo;
-    int ho = (int)(t % Ho);
-    int64_t n = t / Ho;
-    int h0 = ho >> 1, w0 = wo >> 1;
-    int h1 = (ho & 1) ? min(h0 + 1, Hi - 1) : h0;
-    int w1 = (wo & 1) ? min(w0 + 1, Wi - 1) : w0;
-    const T* b = x + n * Hi * Wi * (int64_t)ldx + cv * V;
+    upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Hi, int Wi, idx4_t ix,
+                         uint32_t total) {
+  const int Wo = 2 * Wi;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cv, w0, h0, n;
+    idx4_decode(i, ix, cv, w0, h0, n);
+    const int h1 = min(h0 + 1, Hi - 1), w1 = min(w0 + 1, Wi - 1);
+    const T* b = x + (int64_t)n * Hi * Wi * ldx + cv * V;
     float a[V], bb[V], c[V], d[V], o[V];
     ldv<T, V>(b + ((int64_t)h0 * Wi + w0) * ldx, a);
     ldv<T, V>(b + ((int64_t)h0 * Wi + w1) * ldx, bb);
     ldv<T, V>(b + ((int64_t)h1 * Wi + w0) * ldx, c);
     ldv<T, V>(b + ((int64_t)h1 * Wi + w1) * ldx, d);
+    T* q = y + (((int64_t)n * (2 * Hi) + 2 * h0) * Wo + 2 * w0) * (int64_t)ldy + cv * V;
+    // same operation order as the separable form: along w first (0.5*(l + r), exact when l == r), then along h
+    stv<T, V>(q, a);
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      float top = 0.5f * (a[k] + bb[k]);  // exact when w1 == w0
-      float bot = 0.5f * (c[k] + d[k]);
-      o[k] = 0.5f * (top + bot);
-    }
-    stv<T, V>(y + pix * ldy + cv * V, o);
+    for (int k = 0; k < V; ++k) o[k] = 0.5f * (a[k] + bb[k]);
+    stv<T, V>(q + ldy, o);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = 0.5f * (a[k] + c[k]);
+    stv<T, V>(q + (int64_t)Wo * ldy, o);
+#pragma unroll
+    for (int k = 0; k < V; ++k) o[k] = 0.5f * (0.5f * (a[k] + bb[k]) + 0.5f * (c[k] + d[k]));
+    stv<T, V>(q + (int64_t)Wo * ldy + ldy, o);
   }
 }
 
 // adjoint, gather form: per axis in[k] receives out[2k] (w 1), out[2k+1] (w .5, or 1 when k == n-1), out[2k-1] (w .5, k>=1)
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-    upsample2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, int C,
-                         int64_t total, int accumulate) {
-  const int nvec = C / V;
+    upsample2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, idx4_t ix,
+                         uint32_t total, int accumulate) {
   const int Ho = 2 * Hi, Wo = 2 * Wi;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % nvec);
-    int64_t pix = i / nvec;
-    int w = (int)(pix % Wi);
-    int64_t t = pix / Wi;
-    int h = (int)(t % Hi);
-    int64_t n = t / Hi;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cv, w, h, n;
+    idx4_decode(i, ix, cv, w, h, n);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    const T* b = dy + n * Ho * Wo * (int64_t)lddy + cv * V;
+    const T* b = dy + (int64_t)n * Ho * Wo * lddy + cv * V;
 #pragma unroll
     for (int dh = -1; dh <= 1; ++dh) {
       int ho = 2 * h + dh;
@@ -661,7 +659,7 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < V; ++k) acc[k] += wh * ww * g[k];
       }
     }
-    T* q = dx + pix * lddx + cv * V;
+    T* q = dx + (((int64_t)n * Hi + h) * Wi + w) * (int64_t)lddx + cv * V;
     if (accumulate) {
       float o[V];
       ldv<T, V>(q, o);
@@ -677,10 +675,12 @@ int phs_upsample2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
   PHS_REQUIRE(x->dtype == y->dtype && x->N == y->N && x->C == y->C && y->H == 2 * x->H && y->W == 2 * x->W,
               "phs_upsample2_fwd: shape mismatch");
   int v = min_vec(pick_vec(x), pick_vec(y));
-  int64_t total = (int64_t)y->N * y->H * y->W * (y->C / v);
+  int64_t total = (int64_t)x->N * x->H * x->W * (x->C / v);
+  PHS_REQUIRE(total < (1ll << 31), "phs_upsample2_fwd: tensor too large");
+  const idx4_t ix = idx4_make(x->C / v, x->W, x->H);
   PHS_DISPATCH_DTYPE(x->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (upsample2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, x->H, x->W, x->C, total))));
+                                                (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, x->H, x->W, ix, (uint32_t)total))));
   return phs_check_launch("upsample2_fwd");
 }
 
@@ -690,9 +690,11 @@ int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate
               "phs_upsample2_bwd: shape mismatch");
   int v = min_vec(pick_vec(dx), pick_vec(dy));
   int64_t total = (int64_t)dx->N * dx->H * dx->W * (dx->C / v);
+  PHS_REQUIRE(total < (1ll << 31), "phs_upsample2_bwd: tensor too large");
+  const idx4_t ix = idx4_make(dx->C / v, dx->W, dx->H);
   PHS_DISPATCH_DTYPE(dx->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (upsample2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, dx->C, total,
+                                                (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, ix, (uint32_t)total,
                                                 accumulate))));
   return phs_check_launch("upsample2_bwd");
 }
@@ -750,18 +752,16 @@ int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, i
 // take (forward and filter gradient); one thread per (pixel, 8-channel output vector).
 template <typename T>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ x, int ldx, int Cin, bf16* __restrict__ out,
-                                                        int ldo, int Co, int H, int W, int64_t total) {
-  const int nvec = Co / 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    const int64_t pix = i / nvec;
-    const int wq = (int)(pix % W);
-    const int hq = (int)((pix / W) % H);
+                                                        int ldo, int Co, int H, int W, idx4_t ix, fdiv_t fcin, uint32_t total) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int v, wq, hq, n;
+    idx4_decode(i, ix, v, wq, hq, n);
+    const int64_t pix = ((int64_t)n * H + hq) * W + wq;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = v * 8 + j;
-      const int tap = k / Cin, ci = k - tap * Cin;
+      const int tap = (int)fdiv((uint32_t)k, fcin), ci = k - tap * Cin;
       float val = 0.f;
       if (tap < 9) {
         const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
@@ -780,8 +780,11 @@ int phs_im2col3x3(const phs_tensor* x, const phs_tensor* out, void* stream) {
   PHS_REQUIRE(out->C >= 9 * x->C && x->N == out->N && x->H == out->H && x->W == out->W,
               "phs_im2col3x3: output needs >= 9*Cin channels and the input's N,H,W");
   int64_t total = (int64_t)x->N * x->H * x->W * (out->C / 8);
+  PHS_REQUIRE(total < (1ll << 31), "phs_im2col3x3: tensor too large");
+  const idx4_t ix = idx4_make(out->C / 8, x->W, x->H);
   PHS_DISPATCH_DTYPE(x->dtype, T, (im2col3x3_kernel<T><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                                      (const T*)x->ptr, x->ld, x->C, (bf16*)out->ptr, out->ld, out->C, x->H, x->W, total)));
+                                      (const T*)x->ptr, x->ld, x->C, (bf16*)out->ptr, out->ld, out->C, x->H, x->W, ix,
+                                      fdiv_make((uint32_t)x->C), (uint32_t)total)));
   return phs_check_launch("im2col3x3");
 }
 

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256)
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
     small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                     TO* __restrict__ y, SmallGeom g, int accumulate) {
+                     TO* __restrict__ y, SmallGeom g, int accumulate, idx4_t ix, uint32_t total) {
   extern __shared__ float ws[];  // [tap][Cin][Cout]
   const int taps = g.ks * g.ks;
   for (int i = threadIdx.x; i < taps * g.Cin * g.Cout; i += blockDim.x) {
@@ -125,15 +125,11 @@ __global__ void __launch_bounds__(256)
     ws[i] = wsel(w, g, t, a, b);
   }
   __syncthreads();
-  const int nvec = g.Cout / 8;
-  const int64_t total = (int64_t)g.N * g.H * g.W * nvec;
   const int pad = g.ks / 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % nvec);
-    const int64_t pix = i / nvec;
-    const int wq = (int)(pix % g.W);
-    const int64_t t2 = pix / g.W;
-    const int hq = (int)(t2 % g.H);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int cv, wq, hq, n;
+    idx4_decode(i, ix, cv, wq, hq, n);     // multiply-high index arithmetic: 64-bit divisions made this ALU bound
+    const int64_t pix = ((int64_t)n * g.H + hq) * g.W + wq;
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = bias ? bias[cv * 8 + o] : 0.f;
@@ -361,10 +357,12 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
     const size_t smem = (size_t)taps * x->C * y->C * sizeof(float);
     if (smem > 48 * 1024) return 0;
     int64_t total = M * (y->C / 8);
+    if (total >= (1ll << 31)) return 0;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    const idx4_t ix = idx4_make(y->C / 8, x->W, x->H);
 #define LAUNCH_SI(TI, TO) \
-  small_cin_kernel<TI, TO><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
+  small_cin_kernel<TI, TO><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, ix, (uint32_t)total)
     if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_SI(float, float);
     else if (x->dtype == PHS_F32) LAUNCH_SI(float, bf16);
     else if (y->dtype == PHS_F32) LAUNCH_SI(bf16, float);
