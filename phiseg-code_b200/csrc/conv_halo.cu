@@ -435,7 +435,9 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   const char* e_s = getenv("PHS_HALO_S");
   const char* e_acc = getenv("PHS_HALO_ACC");
   const char* e_g = getenv("PHS_HALO_G");
-  const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") ? 1 : 2);
+  // at most one 128-pixel tile per SM (the 16x16 levels at batch 64): a second CTA slot would stay empty, so the one
+  // CTA gets the whole shared memory = a filter ring deep enough to cover the TMA round trip
+  const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") || total_subs <= num_sms() ? 1 : 2);
   // dynamic shared memory per CTA: 228 KB per SM, 1 KB reserved + ~1.8 KB static per CTA, 1 KB alignment slack
   const int budget_all = ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896;
   const int max_cols = ctas_per_sm == 1 ? 512 : 256;
@@ -452,7 +454,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
       while (S > 1 && (S * y->C > max_cols || subs_w % S != 0)) S /= 2;
     } else {
       while (S * 2 * y->C <= max_cols && subs_w % (S * 2) == 0 &&
-             2 * ((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024 + 4 * b_bytes <= budget &&
+             (getenv("PHS_HALO_NA") ? atoi(getenv("PHS_HALO_NA")) : 2) * (((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024) + 4 * b_bytes <= budget &&
              total_subs / (S * 2) >= min_tiles)
         S *= 2;
     }
@@ -480,8 +482,8 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
       return true;
     }
     p.b_resident = 0;
-    p.na = 2;
-    p.nb = (budget - 2 * (int)p.a_stage_bytes) / b_bytes;
+    p.na = getenv("PHS_HALO_NA") ? atoi(getenv("PHS_HALO_NA")) : 2;
+    p.nb = (budget - p.na * (int)p.a_stage_bytes) / b_bytes;
     if (p.nb > 12) p.nb = 12;
     return p.nb >= 2;
   };

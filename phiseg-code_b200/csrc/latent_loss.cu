@@ -162,6 +162,7 @@ struct XentPtrs {
 // One thread per 2x2 block of full-resolution pixels: the gradients of the coarser levels (nearest-neighbour up-sampled
 // heads: 4^l pixels share one head pixel) are pre-summed over the block, so level 1 needs no atomics at all and levels
 // >= 2 a quarter of them; index arithmetic is multiply-high (idx4_decode).
+template <int NC>   // class slots compiled in (2, 4 or NC): predicated-off slots still cost issue cycles
 __global__ void __launch_bounds__(256)
     xent_multiscale_kernel(XentPtrs P, const uint8_t* __restrict__ labels, int N, int H, int W, int nl, int L,
                            float scale, float* __restrict__ loss_out, idx4_t ix, uint32_t total) {
@@ -172,22 +173,22 @@ __global__ void __launch_bounds__(256)
     int cvu, xb, yb, n;
     idx4_decode(i, ix, cvu, xb, yb, n);
     // coarse-level gradient sums of this block: gblk[l][c] = sum over the block's pixels of prefix_{i<=l} g_i
-    float gblk[XENT_MAXL][XENT_MAXC];
+    float gblk[XENT_MAXL][NC];
 #pragma unroll
     for (int l = 0; l < XENT_MAXL; ++l)
 #pragma unroll
-      for (int c = 0; c < XENT_MAXC; ++c) gblk[l][c] = 0.f;
+      for (int c = 0; c < NC; ++c) gblk[l][c] = 0.f;
 #pragma unroll
     for (int sub = 0; sub < 4; ++sub) {
       const int x = 2 * xb + (sub & 1), y = 2 * yb + (sub >> 1);
       const int64_t p = ((int64_t)n * H + y) * W + x;
       const int lab = labels[p];
-      float acc[XENT_MAXC], gsum[XENT_MAXC];
+      float acc[NC], gsum[NC];
 #pragma unroll
-      for (int c = 0; c < XENT_MAXC; ++c) acc[c] = gsum[c] = 0.f;
+      for (int c = 0; c < NC; ++c) acc[c] = gsum[c] = 0.f;
       // pass 1 (top-down): accumulate logits, per-level loss, per-level softmax gradient g_l;
       // d loss / d logits[j] (at full res) = sum_{i<=j} g_i: walk the levels again bottom-up for the prefix sums
-      float gl[XENT_MAXL][XENT_MAXC];
+      float gl[XENT_MAXL][NC];
 #pragma unroll
       for (int l = XENT_MAXL - 1; l >= 0; --l) {
         if (l < L) {
@@ -195,16 +196,16 @@ __global__ void __launch_bounds__(256)
           const float* src = P.logits[l] + (((int64_t)n * hl + (y >> l)) * wl + (x >> l)) * nl;
           float mx = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < XENT_MAXC; ++c)
+          for (int c = 0; c < NC; ++c)
             if (c < nl) { acc[c] += src[c]; mx = fmaxf(mx, acc[c]); }
           float se = 0.f;
 #pragma unroll
-          for (int c = 0; c < XENT_MAXC; ++c)
+          for (int c = 0; c < NC; ++c)
             if (c < nl) { gl[l][c] = expf(acc[c] - mx); se += gl[l][c]; }
           const float lse = mx + logf(se);
           const float inv = 1.f / se;
 #pragma unroll
-          for (int c = 0; c < XENT_MAXC; ++c)
+          for (int c = 0; c < NC; ++c)
             if (c < nl) {
               gl[l][c] = (gl[l][c] * inv - (c == lab ? 1.f : 0.f)) * scale;
               if (c == lab) lsum[l] += lse - acc[c];
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256)
         for (int l = 0; l < XENT_MAXL; ++l) {
           if (l < L) {
 #pragma unroll
-            for (int c = 0; c < XENT_MAXC; ++c)
+            for (int c = 0; c < NC; ++c)
               if (c < nl) {
                 gsum[c] += gl[l][c];
                 if (l == 0) P.dlogits[0][p * nl + c] = gsum[c];
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(256)
           const int hl = H >> l, wl = W >> l;
           float* dst = P.dlogits[l] + (((int64_t)n * hl + (yb >> (l - 1))) * wl + (xb >> (l - 1))) * nl;
 #pragma unroll
-          for (int c = 0; c < XENT_MAXC; ++c)
+          for (int c = 0; c < NC; ++c)
             if (c < nl) {
               if (l == 1) dst[c] = gblk[l][c];          // the block IS the level-1 pixel
               else atomicAdd(dst + c, gblk[l][c]);
@@ -267,8 +268,15 @@ int phs_xent_multiscale(const float* const* logits, float* const* dlogits, const
   PHS_REQUIRE(nblk < (1ll << 31), "phs_xent_multiscale: tensor too large");
   int blocks = (int)((nblk + 255) / 256 < 148 * 8 ? (nblk + 255) / 256 : 148 * 8);
   const idx4_t ix = idx4_make(1, W / 2, H / 2);
-  xent_multiscale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out, ix,
-                                                                   (uint32_t)nblk);
+  if (nlabels <= 2)
+    xent_multiscale_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out, ix,
+                                                                        (uint32_t)nblk);
+  else if (nlabels <= 4)
+    xent_multiscale_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out, ix,
+                                                                        (uint32_t)nblk);
+  else
+    xent_multiscale_kernel<XENT_MAXC><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale,
+                                                                                loss_out, ix, (uint32_t)nblk);
   return phs_check_launch("xent_multiscale");
 }
 

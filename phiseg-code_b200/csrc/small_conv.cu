@@ -159,6 +159,57 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- 1x1, at most CIN <= 4 input channels -> wide output (the input gradient of the 1x1 heads) -----------------------
+// A thread owns one 8-channel output vector for good: its filter rows live in registers, it walks pixels with four
+// independent loads in flight and does nothing but FMAs and 16-byte stores (no shared memory, no index arithmetic).
+template <typename TI, typename TO, int CIN>
+__global__ void __launch_bounds__(256)
+    small_cin_1x1_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         TO* __restrict__ y, SmallGeom g, int accumulate, int64_t M) {
+  const int nvec = g.Cout / 8;
+  const int PL = blockDim.x / nvec;
+  const int cv = threadIdx.x % nvec, lp = threadIdx.x / nvec;
+  if (lp >= PL) return;
+  float wr[CIN][8], b8[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    b8[o] = bias ? bias[cv * 8 + o] : 0.f;
+#pragma unroll
+    for (int a = 0; a < CIN; ++a) wr[a][o] = a < g.Cin ? wsel(w, g, 0, a, cv * 8 + o) : 0.f;
+  }
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * PL;
+  for (int64_t p = (int64_t)blockIdx.x * PL + lp; p < M; p += U * stride) {
+    float xv[U][CIN];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * stride;
+#pragma unroll
+      for (int a = 0; a < CIN; ++a) xv[u][a] = (q < M && a < g.Cin) ? ldf<TI>(x + q * g.ldx + a) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t q = p + u * stride;
+      if (q >= M) break;
+      float acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        acc[o] = b8[o];
+#pragma unroll
+        for (int a = 0; a < CIN; ++a) acc[o] = fmaf(xv[u][a], wr[a][o], acc[o]);
+      }
+      TO* py = y + q * g.ldy + cv * 8;
+      if (accumulate) {
+        float o8[8];
+        ldv<TO, 8>(py, o8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += o8[k];
+      }
+      stv<TO, 8>(py, acc);
+    }
+  }
+}
+
 // ---- filter gradient with a tiny channel count on one side --------------------------------------------------------
 // dW[t][cs][cw] (small side = x, shifted by the tap)   or   dW[cw][cs] (ksize 1, small side = dy)
 //   = sum_p S[p + t][cs] * Wd[p][cw]
@@ -354,6 +405,24 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
     return rc ? rc : 1;
   }
   if (x->C <= 8 && y->C % 8 == 0 && y->ld % 8 == 0 && ((uintptr_t)y->ptr % (8 * yes > 16 ? 16 : 8 * yes)) == 0) {
+    if (ksize == 1 && x->C <= 4 && y->C / 8 <= 256) {
+      const int nvec = y->C / 8, PL = 256 / nvec;
+      int64_t blocks = (M + (int64_t)PL * 4 - 1) / ((int64_t)PL * 4);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      if (blocks < 1) blocks = 1;
+#define LAUNCH_S1(TI, TO)                                                                                          \
+  do {                                                                                                             \
+    if (x->C <= 2) small_cin_1x1_kernel<TI, TO, 2><<<(int)blocks, 256, 0, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M); \
+    else small_cin_1x1_kernel<TI, TO, 4><<<(int)blocks, 256, 0, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M);          \
+  } while (0)
+      if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_S1(float, float);
+      else if (x->dtype == PHS_F32) LAUNCH_S1(float, bf16);
+      else if (y->dtype == PHS_F32) LAUNCH_S1(bf16, float);
+      else LAUNCH_S1(bf16, bf16);
+#undef LAUNCH_S1
+      int rc1 = phs_check_launch("small_cin_1x1_kernel");
+      return rc1 ? rc1 : 1;
+    }
     const size_t smem = (size_t)taps * x->C * y->C * sizeof(float);
     if (smem > 48 * 1024) return 0;
     int64_t total = M * (y->C / 8);
