@@ -446,6 +446,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   // staged TMA-store epilogue: bf16 outputs that are not accumulated onto, 32-channel granularity
   const bool can_stage = !accumulate && y->dtype == PHS_BF16 && y->C % 32 == 0 && y->ld % 8 == 0 && aligned16(y->ptr) &&
                          !(e_g && atoi(e_g) == 0);
+  int na_pref = getenv("PHS_HALO_NA") ? atoi(getenv("PHS_HALO_NA")) : 2;   // activation (halo) stages when the filter streams
   auto geometry = [&](int G) -> bool {
     const int budget = budget_all - (G ? 2 * 128 * 2 * G : 0);
     int S = 1;
@@ -454,7 +455,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
       while (S > 1 && (S * y->C > max_cols || subs_w % S != 0)) S /= 2;
     } else {
       while (S * 2 * y->C <= max_cols && subs_w % (S * 2) == 0 &&
-             (getenv("PHS_HALO_NA") ? atoi(getenv("PHS_HALO_NA")) : 2) * (((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024) + 4 * b_bytes <= budget &&
+             na_pref * (((TILE_H + 2) * (SUB_W * S * 2 + 2) * ROW + 1023) / 1024 * 1024) + 4 * b_bytes <= budget &&
              total_subs / (S * 2) >= min_tiles)
         S *= 2;
     }
@@ -482,7 +483,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
       return true;
     }
     p.b_resident = 0;
-    p.na = getenv("PHS_HALO_NA") ? atoi(getenv("PHS_HALO_NA")) : 2;
+    p.na = na_pref;
     p.nb = (budget - p.na * (int)p.a_stage_bytes) / b_bytes;
     if (p.nb > 12) p.nb = 12;
     return p.nb >= 2;
@@ -509,6 +510,15 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
     if (e_g && atoi(e_g) != 0 && !ok) ok = geometry(atoi(e_g) == 64 && y->C % 64 == 0 ? 64 : 32);
   }
   if (!ok) ok = geometry(0);
+  // <= 64 output channels with a streamed filter: a [Cout][64] filter tile feeds only 4 short MMAs per sub-tile, so
+  // doubling S (one halo stage instead of two pays for it) beats prefetching the next halo tile (measured: 64x64 64->64
+  // 52 -> 40 us; 128-channel outputs: no gain)
+  if (ok && !p.b_resident && p.S == 1 && y->C <= 64 && na_pref == 2 && !e_s) {
+    const HaloParams keep = p;
+    na_pref = 1;
+    const bool ok1 = geometry(keep.stage_g) && p.S == 2 && !p.b_resident && p.nb >= keep.nb;
+    if (!ok1) { p = keep; na_pref = 2; }
+  }
   if (!ok) return -3;   // caller falls back to the shifted-box kernel
   p.y = y->ptr; p.y_ld = y->ld; p.y_f32 = y->dtype == PHS_F32;
   p.bias = bias;

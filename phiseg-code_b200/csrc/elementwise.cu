@@ -132,22 +132,10 @@ __global__ void __launch_bounds__(RED_THREADS)
   }
 }
 
-// chunks per sample for the grid = (chunks, N) streaming kernels: close to target_blocks / N, nudged so that the
-// N * chunks blocks fill whole waves of 2 resident blocks per SM (these kernels use ~100 registers: 640 blocks on
-// 296 slots is 2.16 waves, i.e. a third wave that is 16% full)
 static int pick_chunks(int N, int target_blocks, int max_chunks) {
-  int base = (target_blocks + N - 1) / N;
-  if (base > max_chunks) base = max_chunks;
-  if (base < 1) base = 1;
-  const int slots = 2 * 148;
-  int best = base;
-  double best_eff = 0.0;
-  for (int c = base; c <= max_chunks && c <= base + base / 2 + 1; ++c) {
-    const int total = N * c;
-    const double eff = (double)total / (double)(((total + slots - 1) / slots) * slots);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
-  }
-  return best;
+  int chunks = (target_blocks + N - 1) / N;
+  if (chunks > max_chunks) chunks = max_chunks;
+  return chunks < 1 ? 1 : chunks;   // (nudging the block count to whole waves was measured: no gain)
 }
 
 static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size_t* smem) {
@@ -155,7 +143,7 @@ static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size
   int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
   int PL = RED_THREADS / CW;
   // aim at >= ~4 blocks per SM overall while keeping >= 64 pixels per pixel-lane where possible
-  int target_blocks = 148 * 8;
+  int target_blocks = 148 * 4;
   int max_chunks = (HW + PL * 8 - 1) / (PL * 8);
   int chunks = pick_chunks(N, target_blocks, max_chunks);
   *ppb = (HW + chunks - 1) / chunks;

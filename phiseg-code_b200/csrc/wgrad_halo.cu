@@ -51,7 +51,7 @@ struct WgradHaloParams {
   float* dw;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -256,11 +256,18 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   const int box_stride = (halo_h * HALO_W * p.slabw * 2 + 1023) / 1024 * 1024;
   if (p.kw_per_acc == 1) p.a_lbo = box_stride;
   const int stage_bytes = box_stride * p.a_boxes + BR_H * BR_W * p.nb * 2;
-  int stages = (SMEM_OPTIN - 2048) / stage_bytes;
+  // Residency decides the grid: with <= 256 TMEM columns and >= 4 stages in half the shared memory two CTAs share an SM
+  // (one CTA's atomics epilogue / pipeline fill overlaps the other's MMAs); otherwise one CTA owns the SM.  The grid is
+  // then exactly ONE wave of resident CTAs (297 CTAs on 148 one-CTA SMs used to run as two waves plus a straggler).
+  const char* e_res = getenv("PHS_WGRAD_CTAS");
+  int resident = (p.tmem_cols <= 256 && (110 * 1024) / stage_bytes >= 4) ? 2 : 1;
+  if (e_res) resident = atoi(e_res) == 2 && p.tmem_cols <= 256 ? 2 : 1;
+  int stages = ((resident == 2 ? 112 * 1024 : SMEM_OPTIN) - 2048) / stage_bytes;
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   const int items = (p.nkh == 3 ? 1 : 3) * p.ci_blocks * p.co_blocks;
-  int splits = (2 * num_sms() + items - 1) / items;
+  int splits = (resident * num_sms()) / items;
   if (splits > p.num_bricks) splits = p.num_bricks;
   if (splits < 1) splits = 1;
   p.bricks_per_split = (p.num_bricks + splits - 1) / splits;

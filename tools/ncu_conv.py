@@ -15,9 +15,12 @@ for (N, H, W, Cin, Cout) in [(64, 128, 128, 128, 128), (64, 128, 128, 32, 32), (
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
     dw = torch.zeros(3, 3, Cin, Cout, device='cuda')
+    stats = torch.zeros(N, Cout, 2, device='cuda')
     for _ in range(2):
         if kind == 'fwd':
             call('phs_conv2d', call.T(x), w, None, call.T(y), 3, 0, 0, L.IMPL_TC)
+        elif kind == 'stats':
+            call('phs_conv2d_stats', call.T(x), w, None, call.T(y), 3, stats)
         else:
             call('phs_conv2d_wgrad', call.T(x), call.T(dy), dw, None, 3, 1, L.IMPL_TC)
     torch.cuda.synchronize()
