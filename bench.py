@@ -36,8 +36,9 @@ CONFIGS = {
     'phiseg_7_5_256': ('phiseg_7_5_256', 32, 256, 4),
 }
 CPU_BATCH = 12   # phiseg/experiments/phiseg_7_5.py:38
-# DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/conv_halo_r01.txt)
-NCU_TRAFFIC = {'128x128 128->128 k3': None}
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel's largest launch, from the
+# committed `ncu --set full` capture profiles/conv_halo_r01.txt ([0]: 300.8 MB read + 229.5 MB written)
+NCU_TRAFFIC = {'128x128 128->128 k3': 530337536}
 
 
 def measured_peaks():
@@ -231,7 +232,7 @@ def main():
     if rank == 0:
         best = None
         for fn, a, name in sp.prog.steps:
-            if fn is not None and name in ('phs_conv2d_stats', 'phs_conv2d'):
+            if fn is not None and name in ('phs_conv2d_stats', 'phs_conv2d_stats_acc', 'phs_conv2d'):
                 xd, yd, k = a[0]._obj, a[3]._obj, a[4]
                 fl = 2.0 * xd.N * xd.H * xd.W * k * k * xd.C * yd.C
                 if best is None or fl > best[0]:
@@ -277,11 +278,11 @@ def main():
         'e2e': {'value': world * batch * args.steps / dt_e2e, 'unit': 'images/s',
                 'h2d_bytes_per_step': int(model.h2d_bytes), 'd2h_bytes_per_step': int(model.d2h_bytes),
                 'ms_per_step': dt_e2e / args.steps * 1e3},
-        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak_tf, 'traffic': None,
-                     'what': 'conv stack of the training step (tcgen05 conv_tc_kernel + wgrad_tc_kernel launches): '
-                             '%.2f algorithmic GFLOP/image x %d images / step time; peak = %s'
-                             % (flop_step / batch / 1e9, batch, peak_src)},
+        'roofline_step': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                          'frac': achieved / peak_tf,
+                          'what': 'whole training step: %.2f algorithmic conv GFLOP/image x %d images / device step time '
+                                  '(every kernel of the step in the denominator); peak = %s'
+                                  % (flop_step / batch / 1e9, batch, peak_src)},
     }
     if kern is not None:
         fl, kt, name, shape, alg_bytes = kern
@@ -289,13 +290,18 @@ def main():
         pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
         if os.path.exists(pk):
             burst = json.load(open(pk)).get('bf16_tflops', burst)
-        line['roofline_kernel'] = {
-            'kernel': 'conv_halo_kernel<64> via %s, %s, batch %d (the largest convolution launch of the step)' % (name, shape, batch),
+        line['roofline'] = {
             'bound': 'tensor', 'achieved': fl / kt / 1e12, 'peak': burst, 'unit': 'TFLOP/s', 'frac': fl / kt / 1e12 / burst,
-            'us_per_launch': kt * 1e6, 'algorithmic_bytes': alg_bytes,
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/conv_halo_r01.txt (ncu --set full)
             'traffic': NCU_TRAFFIC.get(shape),
-            'peak_source': 'measured burst bf16 (MEASURED_PEAKS.json): kernel timed alone'}
+            'kernel': 'conv_halo_kernel<64> (tcgen05 3x3 conv forward + fused norm statistics) via %s, %s, batch %d: '
+                      'the largest launch of the dominant kernel of the step' % (name, shape, batch),
+            'us_per_launch': kt * 1e6, 'algorithmic_flop': fl, 'algorithmic_bytes': alg_bytes,
+            'what': 'algorithmic 2*MACs of the launch / mean of 10 launches timed alone with CUDA events on the launching '
+                    'stream after the timed region (inside the step the launch is a CUDA-graph node and cannot be '
+                    'bracketed); peak = measured burst bf16 (MEASURED_PEAKS.json): kernel timed alone'}
+    if 'roofline' not in line:     # no tensor-core launch in this mode: the step-level figure is all there is
+        line['roofline'] = dict(line['roofline_step'], traffic=None)
     if world == 1 and not args.no_cpu:
         ips, sps, cores = run_cpu_oracle(2, 1)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': cores, 'kind': 'port',

@@ -51,6 +51,10 @@ int phs_conv2d(const phs_tensor* x, const void* w, const float* bias, const phs_
  * channel) sum and sum of squares the following batch_norm / group_norm2D needs: stats[N][C][2] must be zeroed. */
 int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
                      float* stats, void* stream);
+/* Same, for callers that clear the statistics of MANY layers with one fill (the launch-program engine keeps them in one
+ * arena): adds onto stats[N][C][2], which the caller must have zeroed, and launches no memset of its own. */
+int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
+                         float* stats, void* stream);
 /* Conv2DBackpropFilter: dw[kh][kw][ci][co] (+)= sum x[.,h+kh-p,w+kw-p,ci]*dy[.,h,w,co]; db (+)= sum dy (may be NULL).
  * dw/db are float32 in the HWIO master layout.  The TC variant accumulates with atomics: zero or reuse dw first. */
 int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,

@@ -75,6 +75,14 @@ int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, cons
   return conv2d_tc(x, w, bias, y, ksize, 0, 0, stats, (cudaStream_t)stream);
 }
 
+int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
+                         float* stats, void* stream) {
+  int rc = check_conv_args("phs_conv2d_stats_acc", x, w, y, ksize);
+  if (rc) return rc;
+  PHS_REQUIRE(stats, "phs_conv2d_stats_acc: null stats");
+  return conv2d_tc(x, w, bias, y, ksize, 0, 2, stats, (cudaStream_t)stream);
+}
+
 int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,
                      int impl, void* stream) {
   int rc = check_conv_args("phs_conv2d_wgrad", x, dw, dy, ksize);

@@ -417,8 +417,10 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
          y->C <= 256;
 }
 
-int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate,
+int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
                 float* stats, cudaStream_t st) {
+  const int accumulate = accumulate_flags & 1;
+  const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
   const int BK = x->C % 64 == 0 ? 64 : 32;
   const int ROW = BK * 2;
   HaloParams p;
@@ -540,7 +542,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0) + 1024;
   const int ctas = ctas_per_sm * num_sms();
   const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
-  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
+  if (stats && !stats_prezeroed) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<64>, &attr))) return rc;

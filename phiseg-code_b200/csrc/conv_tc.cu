@@ -494,6 +494,8 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
               int accumulate, float* stats, cudaStream_t st) {
   // the gradient w.r.t. the input is the same GEMM on the dgrad filter shadow
   PHS_REQUIRE(x->dtype == PHS_BF16, "conv2d_tc: input must be bf16");
+  const int stats_prezeroed = accumulate & 2;   // bit 1: the caller zeroed stats (phs_conv2d_stats_acc)
+  accumulate &= 1;
   PHS_REQUIRE(x->C % 32 == 0 && y->C % 16 == 0 && y->C >= 16,
               "conv2d_tc: Cin=%d must be a multiple of 32 and Cout=%d a multiple of 16", x->C, y->C);
   if (y->C > 256) {
@@ -517,7 +519,7 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   const int yes = y->dtype == PHS_F32 ? 4 : 2;
   PHS_REQUIRE(((size_t)y->ld * yes) % 16 == 0 && aligned16(y->ptr), "conv2d_tc: output not 16-byte aligned");
   if (conv_halo_eligible(x, y, ksize) && !getenv("PHS_NO_HALO")) {
-    int rc = conv2d_halo(x, w, bias, y, accumulate, stats, st);
+    int rc = conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, stats, st);
     if (rc != -3) return rc;
   }
   if (stats) {
@@ -602,7 +604,8 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
   const int items = taps * p.mblocks;
-  int splits = (2 * num_sms() + items - 1) / items;
+  // ~160 KB of shared memory per CTA: one CTA per SM, so the grid is one wave of at most num_sms CTAs
+  int splits = num_sms() / items;
   if (splits > b.num) splits = b.num;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (b.num + splits - 1) / splits;

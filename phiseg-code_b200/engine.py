@@ -386,6 +386,28 @@ class Program:
         st.lane = 0
         self.steps.append(st)
 
+    def stats_vec(self, n):
+        """Fused-statistics buffer of one layer, carved out of an arena that ONE fill at the start of the program clears
+        (a memset node in front of every convolution sat on the critical path ~100 times per step)."""
+        n = (int(n) + 63) // 64 * 64
+        chunk = 1 << 22
+        if not hasattr(self, '_arena') or self._arena_off + n > self._arena[-1].numel():
+            if not hasattr(self, '_arena'):
+                self._arena = []
+            t = torch.zeros(max(chunk, n), dtype=torch.float32, device=self.device)
+            self._arena.append(t)
+            self.keep.append(t)
+            self.bytes += 4 * t.numel()
+            self._arena_off = 0
+        v = self._arena[-1][self._arena_off:self._arena_off + n]
+        self._arena_off += n
+        return v
+
+    def arena_fills(self):
+        """[(ptr, count)] of the statistics arena chunks (only the used part of the last one)."""
+        ar = getattr(self, '_arena', [])
+        return [(t.data_ptr(), t.numel() if i < len(ar) - 1 else self._arena_off) for i, t in enumerate(ar)]
+
     def vec(self, n, zero=False):
         t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=self.device)
         self.keep.append(t)
@@ -529,11 +551,12 @@ class Builder:
             y = self.new(x.N, x.H, x.W, cout, ydt)
             mode, eps = self._norm_mode()
             N, HW, C = x.N, x.H * x.W, cout
-            stats = pr.vec(N * C * 2)
             fused_stats = tc and mode != L.NORM_BN_INFER
+            stats = pr.stats_vec(N * C * 2) if fused_stats else pr.vec(N * C * 2)
             if fused_stats:
-                # statistics of the following norm come out of the conv epilogue (fp32 accumulators)
-                self.emit('phs_conv2d_stats', x.desc(), w_f, bias, y.desc(), k, stats.data_ptr())
+                # statistics of the following norm come out of the conv epilogue (fp32 accumulators); the arena they
+                # live in is cleared by one fill at the start of the program (build_program)
+                self.emit('phs_conv2d_stats_acc', x.desc(), w_f, bias, y.desc(), k, stats.data_ptr())
             else:
                 self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
             if cfg.norm == 'batch_norm':
@@ -856,6 +879,12 @@ def build_program(cfg, params, B, kind, device):
             sp.argmax = torch.empty((B, H, W), dtype=torch.int64, device=device)
             pr.emit('phs_aggregate_logits', lp, B, H, W, nl, nlev, sp.s_out.data_ptr(), sp.s_out_sm.data_ptr(),
                     sp.sm_accum.data_ptr(), sp.argmax.data_ptr())
+    fills = []
+    for ptr, cnt in pr.arena_fills():
+        st = Step((pr.lib.phs_fill_f32, (ptr, cnt, 0.0), 'phs_fill_f32'))
+        st.lane = 0
+        fills.append(st)
+    pr.steps[0:0] = fills
     sp.n_fwd = len(pr.steps)
     if want_grad:
         b.emit_backward()

@@ -162,3 +162,10 @@ def test_conv_tc_fused_statistics(call, lib, oracle, N, H, W, Cin, Cout):
     # the separate pass sees the bf16-rounded y, the fused epilogue the fp32 accumulators
     assert relerr(stats[..., 0], s_ref) < 5e-3
     assert relerr(stats[..., 1], q_ref) < 5e-3
+    # accumulating variant (the engine clears one arena for all layers): adds onto what the caller left in stats
+    acc = torch.zeros(N, Cout, 2, device='cuda')
+    call('phs_conv2d_stats_acc', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, acc)
+    assert relerr(acc, stats) < 1e-4
+    if H % 16 == 0 and W % 8 == 0:      # halo kernel: really accumulates (other shapes: separate pass, overwrites)
+        call('phs_conv2d_stats_acc', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, acc)
+        assert relerr(acc, 2 * stats) < 1e-4

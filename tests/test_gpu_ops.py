@@ -253,7 +253,7 @@ def _ptrs(ts):
     return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
-@pytest.mark.parametrize('N,H,nl,Lv', [(2, 32, 2, 5), (3, 16, 4, 3), (2, 16, 2, 1)])
+@pytest.mark.parametrize('N,H,nl,Lv', [(2, 32, 2, 5), (3, 16, 4, 3), (2, 16, 2, 1), (2, 8, 6, 2)])
 def test_xent_multiscale(call, oracle, N, H, nl, Lv):
     g = torch.Generator().manual_seed(H + nl)
     logits = [torch.randn(N, H >> l, H >> l, nl, generator=g, dtype=torch.float64).requires_grad_(True) for l in range(Lv)]

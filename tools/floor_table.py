@@ -20,7 +20,7 @@ for r in csv.DictReader(lines):
     sh = [shp(a) for a in args if shp(a)]
     ints = [int(a) for a in args if re.fullmatch(r'-?\d+', a)]
     flop = byt = 0.0
-    if name in ('phs_conv2d', 'phs_conv2d_stats', 'phs_conv2d_wgrad') and len(sh) >= 2:
+    if name in ('phs_conv2d', 'phs_conv2d_stats', 'phs_conv2d_stats_acc', 'phs_conv2d_wgrad') and len(sh) >= 2:
         k = ints[0]
         (px, c0, e0), (_, c1, e1) = sh[0], sh[1]
         flop = 2.0 * px * k * k * c0 * c1

@@ -60,8 +60,8 @@ def main():
     for (fn, a, name), t in zip(steps, med):
         by_kernel[name][0] += t
         by_kernel[name][1] += 1
-        if name in ('phs_conv2d', 'phs_conv2d_wgrad', 'phs_conv2d_stats'):
-            if name == 'phs_conv2d_stats':
+        if name in ('phs_conv2d', 'phs_conv2d_wgrad', 'phs_conv2d_stats', 'phs_conv2d_stats_acc'):
+            if name in ('phs_conv2d_stats', 'phs_conv2d_stats_acc'):
                 xd, yd, k, impl = a[0]._obj, a[3]._obj, a[4], 1
                 kind = 'fwd+stats'
                 cin, cout = xd.C, yd.C
