@@ -588,10 +588,17 @@ class Builder:
                     sums, coef = pr.vec(N * C * 2), pr.vec(N * C * 2)
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
-                    self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
-                              int(relu), sums.data_ptr())
-                    self.emit('phs_norm_bwd_finalize', sums.data_ptr(), stats.data_ptr(), mean.data_ptr(),
-                              rstd.data_ptr(), gamma, N, HW, C, mode, coef.data_ptr(), dgamma, dbeta, dbias, 1)
+                    if mode == L.NORM_BN_TRAIN and dbias is None:
+                        # reduce + finalize in one launch; sums and the block ticket live in the pre-cleared arena
+                        sums = pr.stats_vec(N * C * 2 + 64)
+                        self.emit('phs_norm_bwd_reduce_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
+                                  beta, int(relu), sums.data_ptr(), sums.data_ptr() + 4 * N * C * 2, coef.data_ptr(),
+                                  dgamma, dbeta, 1)
+                    else:
+                        self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
+                                  beta, int(relu), sums.data_ptr())
+                        self.emit('phs_norm_bwd_finalize', sums.data_ptr(), stats.data_ptr(), mean.data_ptr(),
+                                  rstd.data_ptr(), gamma, N, HW, C, mode, coef.data_ptr(), dgamma, dbeta, dbias, 1)
                     self.emit('phs_norm_bwd_apply', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
                               int(relu), coef.data_ptr(), dy.desc())
                     db = None
@@ -879,15 +886,17 @@ def build_program(cfg, params, B, kind, device):
             sp.argmax = torch.empty((B, H, W), dtype=torch.int64, device=device)
             pr.emit('phs_aggregate_logits', lp, B, H, W, nl, nlev, sp.s_out.data_ptr(), sp.s_out_sm.data_ptr(),
                     sp.sm_accum.data_ptr(), sp.argmax.data_ptr())
+    sp.n_fwd = len(pr.steps)
+    if want_grad:
+        b.emit_backward()
+    # one fill per arena chunk in front of everything clears the fused statistics / reduction buffers of ALL layers
     fills = []
     for ptr, cnt in pr.arena_fills():
         st = Step((pr.lib.phs_fill_f32, (ptr, cnt, 0.0), 'phs_fill_f32'))
         st.lane = 0
         fills.append(st)
     pr.steps[0:0] = fills
-    sp.n_fwd = len(pr.steps)
-    if want_grad:
-        b.emit_backward()
+    sp.n_fwd += len(fills)
     sp.conv_flop_fwd = b.n_conv_flop
     return sp
 

@@ -173,10 +173,10 @@ class phiseg():
     # input staging
     # ---------------------------------------------------------------------------------------------------
     def _stage_x(self, sp, x_in):
-        x = np.asarray(x_in, dtype=np.float32)
+        x = np.asarray(x_in)
         if x.shape != tuple(sp.h_x.shape):
             raise ValueError('x has shape %s, expected %s' % (x.shape, tuple(sp.h_x.shape)))
-        sp.h_x.numpy()[...] = x
+        np.copyto(sp.h_x.numpy(), x, casting='unsafe')        # one pass: convert + copy into the pinned buffer
         sp.x.buf.t.copy_(sp.h_x, non_blocking=True)
         return sp.h_x.numel() * 4
 
@@ -184,9 +184,12 @@ class phiseg():
         s = np.asarray(s_in)
         if s.shape != tuple(sp.h_s.shape):
             raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
-        if s.size and (s.min() < 0 or s.max() >= self.cfg.nlabels):
-            raise ValueError('labels must lie in [0, %d)' % self.cfg.nlabels)
-        sp.h_s.numpy()[...] = s.astype(np.uint8)
+        if s.size:
+            # unsigned inputs cannot be negative: one max() pass instead of min() + max()
+            bad = s.max() >= self.cfg.nlabels if s.dtype.kind == 'u' else (s.min() < 0 or s.max() >= self.cfg.nlabels)
+            if bad:
+                raise ValueError('labels must lie in [0, %d)' % self.cfg.nlabels)
+        np.copyto(sp.h_s.numpy(), s, casting='unsafe')
         sp.s.copy_(sp.h_s, non_blocking=True)
         return sp.h_s.numel()
 

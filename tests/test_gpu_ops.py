@@ -163,6 +163,17 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
     # gradient of a conv bias added before the norm = sum over pixels of dy
     close(dbias, y.grad.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-3 * float(y.grad.abs().sum(dim=(0, 1, 2)).max()) + 1e-5,
           what='dbias')
+    if mode == 'bn_train':
+        # fused variant: the last block of the reduction does the finalize (pre-zeroed sums + ticket counter)
+        buf = torch.zeros(N * C * 2 + 64, device='cuda')
+        coef2 = torch.empty(N * C * 2, device='cuda')
+        dgam2 = torch.zeros(C, device='cuda')
+        dbet2 = torch.zeros(C, device='cuda')
+        call('phs_norm_bwd_reduce_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, buf, buf.data_ptr() + 4 * N * C * 2,
+             coef2, dgam2, dbet2, 1)
+        close(coef2, coef.double().cpu(), rtol=1e-5, what='fused coef')
+        close(dgam2, gamma.grad, rtol=2e-4, what='fused dgamma')
+        close(dbet2, beta.grad, rtol=2e-4, what='fused dbeta')
 
 
 # ---------------------------------------------------------------------------------------------------------
