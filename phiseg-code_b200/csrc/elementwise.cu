@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
 
 // sums[n][c] = (sum g*mask, sum g*mask*xhat)
 template <typename T, int V>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_THREADS, 3)
     norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
@@ -181,10 +181,12 @@ __global__ void __launch_bounds__(RED_THREADS)
   }
 }
 
-static int pick_chunks(int N, int target_blocks, int max_chunks) {
-  int chunks = (target_blocks + N - 1) / N;
+// chunks per sample for the grid = (chunks, N) streaming kernels: the largest count whose N * chunks blocks are all
+// resident at once (`slots` = SMs x blocks per SM for the kernel's register use): a single wave, no straggler blocks
+static int pick_chunks(int N, int slots, int max_chunks) {
+  int chunks = slots / N;
   if (chunks > max_chunks) chunks = max_chunks;
-  return chunks < 1 ? 1 : chunks;   // (nudging the block count to whole waves was measured: no gain)
+  return chunks < 1 ? 1 : chunks;
 }
 
 static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size_t* smem) {
@@ -192,9 +194,8 @@ static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size
   int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
   int PL = RED_THREADS / CW;
   // aim at >= ~4 blocks per SM overall while keeping >= 64 pixels per pixel-lane where possible
-  int target_blocks = 148 * 4;
   int max_chunks = (HW + PL * 8 - 1) / (PL * 8);
-  int chunks = pick_chunks(N, target_blocks, max_chunks);
+  int chunks = pick_chunks(N, 148 * 3, max_chunks);     // 80 registers: three blocks per SM
   *ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + *ppb - 1) / *ppb;
   *grid = dim3(chunks, N);
@@ -408,13 +409,12 @@ int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* me
 // 16-byte loads in flight.
 constexpr int STREAM_U = 4;
 
-static void stream_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb) {
+static void stream_geometry(int N, int HW, int C, int V, int blocks_per_sm, dim3* grid, int* ppb) {
   int nvec = C / V;
   int CW = nvec < 256 ? nvec : 256;
   int PL = 256 / CW;
-  int target_blocks = 148 * 8;
   int max_chunks = (HW + PL * STREAM_U - 1) / (PL * STREAM_U);
-  int chunks = pick_chunks(N, target_blocks, max_chunks);
+  int chunks = pick_chunks(N, 148 * blocks_per_sm, max_chunks);
   *ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + *ppb - 1) / *ppb;
   *grid = dim3(chunks, N);
@@ -479,7 +479,7 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
   int v = min_vec(pick_vec(y), pick_vec(a));
   int HW = y->H * y->W;
   dim3 grid; int ppb;
-  stream_geometry(y->N, HW, y->C, v, &grid, &ppb);
+  stream_geometry(y->N, HW, y->C, v, 6, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (norm_act_fwd_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                                 (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, ppb, mean, rstd,
@@ -488,7 +488,7 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
 }
 
 template <typename T, int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     norm_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dy,
                           int lddy, int HW, int C, int pix_per_block, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -565,7 +565,7 @@ int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* me
   int v = min_vec(min_vec(pick_vec(y), pick_vec(g)), pick_vec(dy));
   int HW = y->H * y->W;
   dim3 grid; int ppb;
-  stream_geometry(y->N, HW, y->C, v, &grid, &ppb);
+  stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (norm_bwd_apply_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,

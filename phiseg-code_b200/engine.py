@@ -588,8 +588,10 @@ class Builder:
                     sums, coef = pr.vec(N * C * 2), pr.vec(N * C * 2)
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
-                    if mode == L.NORM_BN_TRAIN and dbias is None:
-                        # reduce + finalize in one launch; sums and the block ticket live in the pre-cleared arena
+                    if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_FUSED_BN_BWD'):
+                        # reduce + finalize in one launch (sums and the block ticket in the pre-cleared arena).  Measured
+                        # neutral-to-slower (13.21 vs 13.17 ms per step: the last block's tail costs what the launch did),
+                        # so it stays opt-in
                         sums = pr.stats_vec(N * C * 2 + 64)
                         self.emit('phs_norm_bwd_reduce_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
                                   beta, int(relu), sums.data_ptr(), sums.data_ptr() + 4 * N * C * 2, coef.data_ptr(),
