@@ -37,8 +37,8 @@ CONFIGS = {
 }
 CPU_BATCH = 12   # phiseg/experiments/phiseg_7_5.py:38
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel's largest launch, from the
-# committed `ncu --set full` capture profiles/conv_halo_r01.txt ([0]: 300.8 MB read + 229.5 MB written)
-NCU_TRAFFIC = {'128x128 128->128 k3': 530337536}
+# committed `ncu --set full` capture profiles/conv_halo_r01.txt ([0]: 300.8 MB read + 229.3 MB written)
+NCU_TRAFFIC = {'128x128 128->128 k3': 530128384}
 
 
 def measured_peaks():
