@@ -52,7 +52,9 @@ int phs_conv2d(const phs_tensor* x, const void* w, const float* bias, const phs_
 int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
                      float* stats, void* stream);
 /* Same, for callers that clear the statistics of MANY layers with one fill (the launch-program engine keeps them in one
- * arena): adds onto stats[N][C][2], which the caller must have zeroed, and launches no memset of its own. */
+ * arena): adds onto stats, which the caller must have zeroed, and launches no memset of its own.  stats holds
+ * (N + 1) * C * 2 floats here: the per-sample sums [N][C][2] followed by the batch totals [C][2] that batch norm needs
+ * (phs_norm_act_fwd_stats reads them). */
 int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
                          float* stats, void* stream);
 /* Conv2DBackpropFilter: dw[kh][kw][ci][co] (+)= sum x[.,h+kh-p,w+kw-p,ci]*dy[.,h,w,co]; db (+)= sum dy (may be NULL).
@@ -67,6 +69,12 @@ int phs_chan_stats(const phs_tensor* y, float* stats, void* stream);
  * Bessel-corrected variance; infer: moving statistics) or group_norm2D (groups of C/max(2,C/16) channels). */
 int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
                       float* moving_var, float* mean, float* rstd, void* stream);
+/* phs_norm_finalize + phs_norm_act_fwd in one launch, for training-mode batch_norm and for group_norm2D: mean / rstd are
+ * derived inside the kernel from the phs_conv2d_stats_acc layout ((N + 1) * C * 2 floats), written to mean/rstd[N][C] for
+ * the backward kernels, and the batch-norm moving averages are updated (decay; may be NULL for group norm). */
+int phs_norm_act_fwd_stats(const phs_tensor* y, const float* stats, int mode, float eps, float decay, float* moving_mean,
+                           float* moving_var, float* mean, float* rstd, const float* gamma, const float* beta, int relu,
+                           const phs_tensor* a, void* stream);
 /* a = act(gamma*(y-mean)*rstd + beta); relu != 0 applies tf.nn.relu (tfwrapper/layers.py:134-135). */
 int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                      int relu, const phs_tensor* a, void* stream);

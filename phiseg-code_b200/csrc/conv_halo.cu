@@ -44,6 +44,7 @@ struct HaloParams {
   const float* bias;
   int accumulate;
   float* stats;               // [N][Cout][2] or null
+  float* totals;              // [Cout][2] batch totals (phs_conv2d_stats_acc layout) or null
   int stage_g;                // 0: direct register -> global stores; 32 | 64: channels per smem-staged TMA store group
   long long* trace;           // PHS_HALO_TRACE: per-role clock64 stamps of the first CTAs (tools/trace_halo.py)
   int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
@@ -275,6 +276,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (j * 16 < p.Cout) {
             const int c = j * 16 + col16(lane);
             atomicAdd(dst + c * 2 + (lane & 1), (lane & 1) ? st_q[j] : st_s[j]);
+            if (p.totals) atomicAdd(p.totals + c * 2 + (lane & 1), (lane & 1) ? st_q[j] : st_s[j]);
             st_s[j] = st_q[j] = 0.f;
           }
       }
@@ -529,6 +531,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   p.bias = bias;
   p.accumulate = accumulate;
   p.stats = stats;
+  p.totals = (stats && stats_prezeroed) ? stats + (size_t)x->N * y->C * 2 : nullptr;
   {
     const char* e = getenv("PHS_HALO_DBG");
     p.dbg = e ? atoi(e) : 0;

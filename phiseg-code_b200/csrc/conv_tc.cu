@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(256) bias_grad_bf16_kernel(const bf16* __restr
 // dispatch
 // ------------------------------------------------------------------------------------------------------------
 bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize);
+int chan_stats_run(const phs_tensor* y, float* stats, bool with_totals, bool zero_first, cudaStream_t st);
 int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate, float* stats,
                 cudaStream_t st);
 bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
@@ -526,7 +527,7 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
     // shapes the halo kernel does not take: plain convolution, then a separate statistics pass over y
     int rc = conv2d_tc(x, w, bias, y, ksize, dgrad, accumulate, nullptr, st);
     if (rc) return rc;
-    return phs_chan_stats(y, stats, st);
+    return chan_stats_run(y, stats, stats_prezeroed != 0, !stats_prezeroed, st);
   }
   const int BK = x->C % 64 == 0 ? 64 : 32;
   const int taps = ksize * ksize;

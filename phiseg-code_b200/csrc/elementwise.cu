@@ -27,7 +27,8 @@ struct BwdFin {
 
 template <typename T, int V>
 __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __restrict__ y, int HW, int C, int ld,
-                                                                 int pix_per_block, float* __restrict__ stats) {
+                                                                 int pix_per_block, float* __restrict__ stats,
+                                                                 float* __restrict__ totals) {
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
     float a = 0.f;
     for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
     atomicAdd(&stats[(size_t)n * C * 2 + i], a);
+    if (totals) atomicAdd(&totals[i], a);
   }
 }
 
@@ -202,18 +204,24 @@ static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size
   *smem = (size_t)PL * C * 2 * sizeof(float);
 }
 
-int phs_chan_stats(const phs_tensor* y, float* stats, void* stream) {
-  PHS_REQUIRE(y && y->ptr && stats, "phs_chan_stats: null argument");
-  cudaStream_t st = (cudaStream_t)stream;
+// stats[N][C][2] (+)= per-sample sums; with_totals: the [C][2] batch totals that follow them are accumulated too
+// (layout of phs_conv2d_stats_acc); zero_first: clear the per-sample part (the plain phs_chan_stats contract)
+int chan_stats_run(const phs_tensor* y, float* stats, bool with_totals, bool zero_first, cudaStream_t st) {
   int HW = y->H * y->W;
-  cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
+  if (zero_first) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
   int v = pick_vec(y);
   dim3 grid; int ppb; size_t smem;
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_chan_stats: C=%d too large", y->C);
+  float* totals = with_totals ? stats + (size_t)y->N * y->C * 2 : nullptr;
   PHS_DISPATCH_DTYPE(y->dtype, T, PHS_DISPATCH_VEC(v, V, (chan_stats_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
-                                                            (const T*)y->ptr, HW, y->C, y->ld, ppb, stats))));
+                                                            (const T*)y->ptr, HW, y->C, y->ld, ppb, stats, totals))));
   return phs_check_launch("chan_stats");
+}
+
+int phs_chan_stats(const phs_tensor* y, float* stats, void* stream) {
+  PHS_REQUIRE(y && y->ptr && stats, "phs_chan_stats: null argument");
+  return chan_stats_run(y, stats, false, true, (cudaStream_t)stream);
 }
 
 int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
@@ -469,6 +477,117 @@ __global__ void __launch_bounds__(256)
       stv<T, V>(ab + (size_t)p * lda + cv * V, v);
     }
   }
+}
+
+// norm_finalize folded into norm_act_fwd: every thread derives mean / rstd of its V channels from the statistics the
+// convolution epilogue left behind (batch norm: the [C][2] batch totals behind stats[N][C][2]; group norm: the sums of
+// its group of sample n), so the forward chain of a layer is conv -> this kernel.  The blocks with blockIdx.x == 0 also
+// write mean/rstd[N][C] for the backward kernels, block (0, 0) updates the batch-norm moving averages.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    norm_act_fwd_stats_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C,
+                              int pix_per_block, const float* __restrict__ stats, int mode, float eps, float decay,
+                              float* moving_mean, float* moving_var, float* __restrict__ mean_out,
+                              float* __restrict__ rstd_out, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, int relu) {
+  const int n = blockIdx.y, N = gridDim.y;
+  const int nvec = C / V;
+  const int CW = nvec < 256 ? nvec : 256;
+  const int PL = 256 / CW;
+  const int lane_c = threadIdx.x % CW, lane_p = threadIdx.x / CW;
+  if (lane_p >= PL) return;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const T* yb = y + (size_t)n * HW * ldy;
+  T* ab = a + (size_t)n * HW * lda;
+  const float* totals = stats + (size_t)N * C * 2;
+  const int G = max(2, C / 16), cpg = C / G;
+  for (int cv = lane_c; cv < nvec; cv += CW) {
+    float sc[V], sh[V];
+    int g_cached = -1;
+    double g_m = 0.0, g_r = 0.0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int c = cv * V + k;
+      double m, r;
+      if (mode == PHS_NORM_GN) {
+        const int grp = c / cpg;
+        if (grp != g_cached) {
+          double s = 0.0, q = 0.0;
+          const float* gs = stats + ((size_t)n * C + (size_t)grp * cpg) * 2;
+          for (int i = 0; i < cpg; ++i) { s += gs[2 * i]; q += gs[2 * i + 1]; }
+          const double cnt = (double)HW * cpg;
+          g_m = s / cnt;
+          double var = q / cnt - g_m * g_m;
+          if (var < 0) var = 0;
+          g_r = 1.0 / sqrt(var + (double)eps);
+          g_cached = grp;
+        }
+        m = g_m; r = g_r;
+      } else {
+        const double cnt = (double)HW * N;
+        m = (double)totals[2 * c] / cnt;
+        double var = (double)totals[2 * c + 1] / cnt - m * m;
+        if (var < 0) var = 0;
+        r = 1.0 / sqrt(var + (double)eps);
+        if (moving_mean && blockIdx.x == 0 && n == 0 && lane_p == 0) {
+          const double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+          moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * (float)m;
+          moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)unb;
+        }
+      }
+      if (blockIdx.x == 0 && lane_p == 0) {
+        mean_out[(size_t)n * C + c] = (float)m;
+        rstd_out[(size_t)n * C + c] = (float)r;
+      }
+      sc[k] = gamma[c] * (float)r;
+      sh[k] = beta[c] - (float)m * sc[k];
+    }
+    int p = p0 + lane_p;
+    for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
+      float v[STREAM_U][V];
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) ldv<T, V>(yb + (size_t)(p + u * PL) * ldy + cv * V, v[u]);
+#pragma unroll
+      for (int u = 0; u < STREAM_U; ++u) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float r = fmaf(v[u][k], sc[k], sh[k]);
+          v[u][k] = (relu && r < 0.f) ? 0.f : r;
+        }
+        stv<T, V>(ab + (size_t)(p + u * PL) * lda + cv * V, v[u]);
+      }
+    }
+    for (; p < p1; p += PL) {
+      float v[V];
+      ldv<T, V>(yb + (size_t)p * ldy + cv * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float r = fmaf(v[k], sc[k], sh[k]);
+        v[k] = (relu && r < 0.f) ? 0.f : r;
+      }
+      stv<T, V>(ab + (size_t)p * lda + cv * V, v);
+    }
+  }
+}
+
+int phs_norm_act_fwd_stats(const phs_tensor* y, const float* stats, int mode, float eps, float decay, float* moving_mean,
+                           float* moving_var, float* mean, float* rstd, const float* gamma, const float* beta, int relu,
+                           const phs_tensor* a, void* stream) {
+  PHS_REQUIRE(y && a && y->ptr && a->ptr && stats && mean && rstd && gamma && beta, "phs_norm_act_fwd_stats: null argument");
+  PHS_REQUIRE(y->dtype == a->dtype && y->N == a->N && y->H == a->H && y->W == a->W && y->C == a->C,
+              "phs_norm_act_fwd_stats: y/a mismatch");
+  PHS_REQUIRE(mode == PHS_NORM_GN || mode == PHS_NORM_BN_TRAIN, "phs_norm_act_fwd_stats: mode %d needs phs_norm_finalize", mode);
+  PHS_REQUIRE(mode != PHS_NORM_GN || y->C % max(2, y->C / 16) == 0, "phs_norm_act_fwd_stats: C=%d not divisible into groups", y->C);
+  int v = min_vec(pick_vec(y), pick_vec(a));
+  int HW = y->H * y->W;
+  dim3 grid; int ppb;
+  stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);   // 77 registers: three blocks per SM
+  PHS_DISPATCH_DTYPE(y->dtype, T,
+                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_stats_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                                                (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, ppb, stats, mode, eps,
+                                                decay, moving_mean, moving_var, mean, rstd, gamma, beta, relu))));
+  return phs_check_launch("norm_act_fwd_stats");
 }
 
 int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, const float* gamma, const float* beta,

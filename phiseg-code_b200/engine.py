@@ -552,7 +552,7 @@ class Builder:
             mode, eps = self._norm_mode()
             N, HW, C = x.N, x.H * x.W, cout
             fused_stats = tc and mode != L.NORM_BN_INFER
-            stats = pr.stats_vec(N * C * 2) if fused_stats else pr.vec(N * C * 2)
+            stats = pr.stats_vec((N + 1) * C * 2) if fused_stats else pr.vec(N * C * 2)
             if fused_stats:
                 # statistics of the following norm come out of the conv epilogue (fp32 accumulators); the arena they
                 # live in is cleared by one fill at the start of the program (build_program)
@@ -570,12 +570,17 @@ class Builder:
                 dgamma, dbeta = P.ptr(pre + 'gamma', 'g'), P.ptr(pre + 'beta', 'g')
                 mm = mv = None
             mean, rstd = pr.vec(N * C), pr.vec(N * C)
-            if mode != L.NORM_BN_INFER and not fused_stats:
-                self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
-            self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
-                      rstd.data_ptr())
             a = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
-            self.emit('phs_norm_act_fwd', y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+            if fused_stats:
+                # finalize folded into the activation kernel (mean / rstd still land in their arrays for the backward)
+                self.emit('phs_norm_act_fwd_stats', y.desc(), stats.data_ptr(), mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
+                          rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+            else:
+                if mode != L.NORM_BN_INFER:
+                    self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
+                self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
+                          rstd.data_ptr())
+                self.emit('phs_norm_act_fwd', y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
             nb = (mode, stats, mean, rstd, gamma, beta, dgamma, dbeta)
 
         if self.want_grad:

@@ -132,6 +132,7 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
     eps = 1e-5 if mode == 'gn' else 1e-3
     yd, gd, bd = cu(y, torch.float32), cu(gamma, torch.float32), cu(beta, torch.float32)
     mmd, mvd = cu(mm, torch.float32), cu(mv, torch.float32)
+    mmd2, mvd2 = mmd.clone(), mvd.clone()
     stats = torch.empty(N * C * 2, device='cuda')
     mean = torch.empty(N * C, device='cuda')
     rstd = torch.empty(N * C, device='cuda')
@@ -147,6 +148,17 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
         close(mvd, ns['s/BatchNorm/moving_variance'], what='moving variance (Bessel corrected)')
     if mode == 'bn_infer':
         return
+    # finalize folded into the activation kernel: per-sample sums followed by the batch totals (phs_conv2d_stats_acc layout)
+    stats2 = torch.cat([stats, stats.view(N, C, 2).sum(dim=0).reshape(-1)]).contiguous()
+    mean2, rstd2, ad2 = torch.empty_like(mean), torch.empty_like(rstd), torch.empty_like(yd)
+    call('phs_norm_act_fwd_stats', call.T(yd), stats2, lmode, eps, 0.99, mmd2 if mode == 'bn_train' else None,
+         mvd2 if mode == 'bn_train' else None, mean2, rstd2, gd, bd, 1, call.T(ad2))
+    close(ad2, ref, what='fused finalize + norm + relu fwd')
+    close(mean2, mean, rtol=1e-6, what='fused mean')
+    close(rstd2, rstd, rtol=1e-6, what='fused rstd')
+    if mode == 'bn_train':
+        close(mmd2, mmd, rtol=1e-6, what='fused moving mean')
+        close(mvd2, mvd, rtol=1e-6, what='fused moving variance')
     gad = cu(ga, torch.float32)
     sums = torch.empty(N * C * 2, device='cuda')
     coef = torch.empty(N * C * 2, device='cuda')
