@@ -480,7 +480,7 @@ class Builder:
         # filter gradients hang off the backward chain (nothing but the optimizer consumes them): they go to their own
         # lane so the tensor-bound wgrad kernels overlap the HBM-bound normalisation adjoints of the layers below
         self.wlane = 3 if (self.use_lanes and os.environ.get('PHS_NO_WLANE') is None) else None
-        self.wlane_used = False
+        self.wlanes_used = set()
 
     # -- helpers ------------------------------------------------------------------------------------------
     def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
@@ -614,9 +614,11 @@ class Builder:
                     db = P.ptr(scope + '/b', 'g') if bias is not None else None
                 lane = self.lane
                 if self.wlane is not None:
-                    pr.emit_after(lane, self.wlane)
-                    self.lane = self.wlane
-                    self.wlane_used = True
+                    # one filter-gradient lane per origin lane: the two encoders' gradients do not queue behind each other
+                    wl = self.wlane + (lane if (lane in (1, 2) and os.environ.get('PHS_WLANES', '3') != '1') else 0)
+                    pr.emit_after(lane, wl)
+                    self.lane = wl
+                    self.wlanes_used.add(wl)
                 if pad_in:
                     scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
                     self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
@@ -682,8 +684,8 @@ class Builder:
             self.lane = getattr(f, 'lane', 0)
             f()
         self.lane = 0
-        if self.wlane_used:
-            self.prog.emit_sync('join', [self.wlane])
+        if self.wlanes_used:
+            self.prog.emit_sync('join', sorted(self.wlanes_used))
         self.tape = []
 
 
