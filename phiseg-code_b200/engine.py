@@ -967,8 +967,19 @@ def _phiseg_merge(b, cfg, post_z, cat):
         b.conv(u, 'likelihood/post_z%d_ups_c' % (i + 1), 3, nc[i], out=cat[i].act(nc[i], nc[i]))
         h = b.conv(cat[i].act(), 'likelihood/post_c_%d_1' % i, 3, nc[i + d])
         post_c[i] = b.conv(h, 'likelihood/post_c_%d_2' % i, 3, nc[i + d])
-    return [b.conv(post_c[i], 'likelihood/y_lvl%d' % i, 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32)
-            for i in range(Lv)]
+    # the per-level heads are independent of each other (1x1 convolutions onto nlabels channels, HBM bound): levels >= 1
+    # run on their own lanes next to the big level-0 head, forward and (mirrored) backward
+    side = [10 + i for i in range(1, Lv)] if b.use_lanes else []
+    if side:
+        b.fork(side)
+    outs = []
+    for i in range(Lv):
+        b.set_lane(10 + i if (side and i > 0) else 0)
+        outs.append(b.conv(post_c[i], 'likelihood/y_lvl%d' % i, 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32))
+    if side:
+        b.join(side)
+    b.set_lane(0)
+    return outs
 
 
 def _phiseg_likelihood(b, cfg, z):
