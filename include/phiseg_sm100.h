@@ -57,6 +57,11 @@ int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, cons
  * (phs_norm_act_fwd_stats reads them). */
 int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
                          float* stats, void* stream);
+/* Host-only introspection (no device work, callable without a GPU): the launch geometry the halo-tile tcgen05 kernel
+ * would use for a 3x3 layer.  plan[12] = {CTAs per SM, S, halo stages, filter stages, filter resident, staging group,
+ * accumulator stages, TMEM columns, dynamic shared memory bytes, grid, tiles, BK}; accumulate bit 1 = statistics buffer
+ * pre-zeroed.  Returns 1 if that kernel takes the layer, 0 if another kernel does. */
+int phs_conv_halo_plan(const phs_tensor* x, const phs_tensor* y, int accumulate, int with_stats, int* plan);
 /* Conv2DBackpropFilter: dw[kh][kw][ci][co] (+)= sum x[.,h+kh-p,w+kw-p,ci]*dy[.,h,w,co]; db (+)= sum dy (may be NULL).
  * dw/db are float32 in the HWIO master layout.  The TC variant accumulates with atomics: zero or reuse dw first. */
 int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,

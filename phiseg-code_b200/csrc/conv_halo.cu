@@ -422,8 +422,9 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
          y->C <= 256;
 }
 
-int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
-                float* stats, cudaStream_t st) {
+// plan_out != nullptr: only choose the geometry and report it (phs_conv_halo_plan), nothing is launched
+static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
+                          float* stats, cudaStream_t st, int* plan_out) {
   const int accumulate = accumulate_flags & 1;
   const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
   const int BK = x->C % 64 == 0 ? 64 : 32;
@@ -538,6 +539,15 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
     const char* t = getenv("PHS_HALO_TRACE");
     p.trace = t ? (long long*)strtoull(t, nullptr, 0) : nullptr;
   }
+  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0) + 1024;
+  const int ctas = ctas_per_sm * num_sms();
+  const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
+  if (plan_out) {
+    const int v[12] = {ctas_per_sm, p.S, p.na, p.nb, p.b_resident, p.stage_g, p.acc_stages, p.tmem_cols, smem, grid,
+                       p.num_tiles, BK};
+    for (int i = 0; i < 12; ++i) plan_out[i] = v[i];
+    return 0;
+  }
   CUtensorMap tmA, tmB;
   int rc = activation_map(x, BK, SUB_W * p.S + 2, TILE_H + 2, 1, &tmA);
   if (rc) return rc;
@@ -545,9 +555,6 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
   if (rc) return rc;
   CUtensorMap tmY = tmA;
   if (p.stage_g && (rc = activation_map(y, p.stage_g, SUB_W, TILE_H, 1, &tmY))) return rc;
-  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0) + 1024;
-  const int ctas = ctas_per_sm * num_sms();
-  const int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   if (stats && !stats_prezeroed) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
   if (BK == 64) {
     static bool attr = false;
@@ -559,4 +566,21 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
     conv_halo_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, tmY, p);
   }
   return phs_check_launch("conv_halo_kernel");
+}
+
+int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
+                float* stats, cudaStream_t st) {
+  return conv_halo_impl(x, w, bias, y, accumulate_flags, stats, st, nullptr);
+}
+
+// Host-only: the launch geometry conv2d_halo would choose for this layer (no device work; usable without a GPU, the SM
+// count then defaults to 148).  plan[12] = {CTAs per SM, S, halo stages, filter stages, filter resident, staging group,
+// accumulator stages, TMEM columns, dynamic shared memory, grid, tiles, BK}.  Returns 1 if the halo kernel takes the
+// layer, 0 if it does not (other kernels do), <0 on bad arguments.
+extern "C" int phs_conv_halo_plan(const phs_tensor* x, const phs_tensor* y, int accumulate, int with_stats, int* plan) {
+  PHS_REQUIRE(x && y && plan, "phs_conv_halo_plan: null argument");
+  if (!conv_halo_eligible(x, y, 3)) return 0;
+  static float dummy_stats;
+  int rc = conv_halo_impl(x, nullptr, nullptr, y, accumulate, with_stats ? &dummy_stats : nullptr, nullptr, plan);
+  return rc == 0 ? 1 : (rc == -3 ? 0 : rc);
 }
