@@ -62,6 +62,10 @@ int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, 
  * accumulator stages, TMEM columns, dynamic shared memory bytes, grid, tiles, BK}; accumulate bit 1 = statistics buffer
  * pre-zeroed.  Returns 1 if that kernel takes the layer, 0 if another kernel does. */
 int phs_conv_halo_plan(const phs_tensor* x, const phs_tensor* y, int accumulate, int with_stats, int* plan);
+/* Same for the halo-tile filter-gradient kernel.  plan[12] = {resident CTAs per SM, filter rows per CTA, accumulators per
+ * filter row, output channels per CTA, input-channel blocks, output-channel blocks, pipeline stages, TMEM columns,
+ * dynamic shared memory bytes, work items (grid.x), brick splits (grid.y), bricks per split}. */
+int phs_wgrad_halo_plan(const phs_tensor* x, const phs_tensor* dy, int* plan);
 /* Conv2DBackpropFilter: dw[kh][kw][ci][co] (+)= sum x[.,h+kh-p,w+kw-p,ci]*dy[.,h,w,co]; db (+)= sum dy (may be NULL).
  * dw/db are float32 in the HWIO master layout.  The TC variant accumulates with atomics: zero or reuse dw first. */
 int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,

@@ -207,7 +207,8 @@ bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize) {
 }
 
 // dw must already hold the values to accumulate onto (the caller zeroes it when accumulate == 0)
-int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st) {
+// plan_out != nullptr: only choose the geometry and report it (phs_wgrad_halo_plan), nothing is launched
+static int wgrad_halo_impl(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st, int* plan_out) {
   WgradHaloParams p;
   p.N = x->N; p.H = x->H; p.W = x->W; p.Cin = x->C; p.Cout = dy->C;
   p.bricksW = x->W / BR_W;
@@ -272,6 +273,12 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   if (splits < 1) splits = 1;
   p.bricks_per_split = (p.num_bricks + splits - 1) / splits;
   splits = (p.num_bricks + p.bricks_per_split - 1) / p.bricks_per_split;
+  if (plan_out) {
+    const int v[12] = {resident, p.nkh, p.n_acc, p.nb, p.ci_blocks, p.co_blocks, stages, p.tmem_cols,
+                       stages * stage_bytes + 2048, items, splits, p.bricks_per_split};
+    for (int i = 0; i < 12; ++i) plan_out[i] = v[i];
+    return 0;
+  }
   CUtensorMap tmX, tmDY;
   int rc = activation_map(x, p.slabw, HALO_W, halo_h, 1, &tmX);
   if (rc) return rc;
@@ -282,4 +289,17 @@ int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cuda
   const int smem = stages * stage_bytes + 2048;
   wgrad_halo_kernel<<<dim3(items, splits), 192, smem, st>>>(tmX, tmDY, p);
   return phs_check_launch("wgrad_halo_kernel");
+}
+
+int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st) {
+  return wgrad_halo_impl(x, dy, dw, st, nullptr);
+}
+
+// Host-only (no device work): the geometry conv2d_wgrad_halo would choose.  plan[12] = {resident CTAs per SM, filter rows
+// per CTA, accumulators per filter row, output channels per CTA, input-channel blocks, output-channel blocks, pipeline
+// stages, TMEM columns, dynamic shared memory, work items (grid.x), brick splits (grid.y), bricks per split}.
+extern "C" int phs_wgrad_halo_plan(const phs_tensor* x, const phs_tensor* dy, int* plan) {
+  PHS_REQUIRE(x && dy && plan, "phs_wgrad_halo_plan: null argument");
+  if (!wgrad_halo_eligible(x, dy, 3)) return 0;
+  return wgrad_halo_impl(x, dy, nullptr, nullptr, plan) == 0 ? 1 : -1;
 }

@@ -33,6 +33,7 @@ SIGNATURES = {
     'phs_conv2d_stats': [_T, _P, _P, _T, c_int, _P, _S],
     'phs_conv2d_stats_acc': [_T, _P, _P, _T, c_int, _P, _S],
     'phs_conv_halo_plan': [_T, _T, c_int, c_int, POINTER(c_int)],
+    'phs_wgrad_halo_plan': [_T, _T, POINTER(c_int)],
     'phs_conv2d_wgrad': [_T, _T, _P, _P, c_int, c_int, c_int, _S],
     'phs_chan_stats': [_T, _P, _S],
     'phs_norm_finalize': [_P, c_int, c_int, c_int, c_int, c_float, c_float, _P, _P, _P, _P, _S],

@@ -55,3 +55,27 @@ def test_halo_plan_declines_what_it_cannot_take(lib):
     assert _plan(lib, 4, 8, 8, 64, 64, False)[0] == 0          # image smaller than one 16x8 tile: shifted-box kernel
     assert _plan(lib, 4, 32, 32, 64, 8, False)[0] == 0         # 8 output channels: small-channel kernel
     assert _plan(lib, 4, 32, 32, 48, 64, False)[0] == 0        # Cin not a multiple of 32
+
+
+@pytest.mark.parametrize('N,res', [(64, 128), (64, 64), (64, 16), (32, 256), (3, 32), (512, 128)])
+def test_wgrad_halo_geometry_is_one_resident_wave(lib, N, res):
+    h = lib.load()
+    for cin, cout in PAIRS:
+        if cout > 256:
+            continue
+        x = lib.phs_tensor(None, N, res, res, cin, cin, lib.PHS_BF16)
+        dy = lib.phs_tensor(None, N, res, res, cout, cout, lib.PHS_BF16)
+        out = (ctypes.c_int * 12)()
+        rc = h.phs_wgrad_halo_plan(ctypes.byref(x), ctypes.byref(dy), out)
+        assert rc == 1, (cin, cout, rc)
+        resident, nkh, n_acc, nb, cib, cob, stages, tmem, smem, items, splits, bps = list(out)
+        tag = (N, res, cin, cout, list(out))
+        bricks = N * (res // 16) * (res // 8)
+        assert resident in (1, 2) and nkh in (1, 3) and stages >= 2, tag
+        assert smem + 208 + 1024 <= SM_SMEM // resident, tag
+        assert tmem in (32, 64, 128, 256, 512) and nkh * n_acc * nb <= tmem and tmem * resident <= 512, tag
+        assert nb % 32 == 0 and nb * cob == cout and cib == (cin + 127) // 128 or cin in (32, 64), tag
+        assert items == (1 if nkh == 3 else 3) * cib * cob, tag
+        assert splits * bps >= bricks and (splits - 1) * bps < bricks, tag      # every brick exactly once
+        # one wave of resident CTAs (the point of sizing the grid by residency), unless there are more items than slots
+        assert items * splits <= max(resident * 148, items), tag
