@@ -1,0 +1,103 @@
+"""CPU checks of the launch-program builder (engine.build_program): programs are built on the CPU device (nothing is
+launched) and their structure is checked - lane discipline (every launch on a lane that has been forked or chained,
+every side lane joined before the program ends: what CUDA-graph capture requires), the single arena fill in front, one
+filter-gradient launch per live convolution writing into its own slot of the flat gradient buffer, and the algorithmic
+FLOP count of SURVEY.md section 8d."""
+import collections
+import importlib
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope='module')
+def E(pkg):
+    return importlib.import_module('phiseg_code_b200.engine')
+
+
+def _build(E, arch, kind, size=64, B=2, norm='batch_norm', nlabels=2):
+    kw = dict(arch=arch, image_size=(size, size, 1), mode='fast', norm=norm, nlabels=nlabels)
+    if arch == 'probunet':
+        kw.update(zdim0=6, latent_levels=1)
+    cfg = E.NetConfig(**kw)
+    P = E.Params(cfg, torch.device('cpu'))
+    return cfg, P, E.build_program(cfg, P, B, kind, torch.device('cpu'))
+
+
+def _check_lanes(steps):
+    live = {0}
+    dirty = set()
+    for st in steps:
+        fn, args, name = st
+        if fn is None:
+            if name == 'fork':
+                for ln in args[0]:
+                    live.add(ln)
+                    dirty.add(ln)
+            elif name == 'join':
+                for ln in args[0]:
+                    assert ln in live, 'join of a lane that was never forked: %s' % (ln,)
+                    dirty.discard(ln)
+            elif name == 'after':
+                src, dst = args[0]
+                assert src in live, 'dependency on an unknown lane %d' % src
+                live.add(dst)
+                dirty.add(dst)
+            else:
+                raise AssertionError('unknown sync step %r' % name)
+            continue
+        lane = getattr(st, 'lane', 0)
+        assert lane in live, '%s launched on lane %d outside a fork / after' % (name, lane)
+        if lane != 0:
+            dirty.add(lane)
+    assert not dirty, 'side lanes never joined: %s' % sorted(dirty)
+
+
+@pytest.mark.parametrize('arch,kind,norm', [('phiseg', 'train', 'batch_norm'), ('phiseg', 'train', 'group_norm'),
+                                            ('phiseg', 'eval', 'batch_norm'), ('phiseg', 'sample', 'batch_norm'),
+                                            ('phiseg', 'posterior', 'group_norm'), ('phiseg', 'from_z', 'batch_norm'),
+                                            ('probunet', 'train', 'batch_norm'), ('probunet', 'sample', 'group_norm')])
+def test_programs_keep_lane_discipline(E, arch, kind, norm):
+    cfg, P, sp = _build(E, arch, kind, norm=norm)
+    _check_lanes(sp.prog.steps)
+    # the forward part alone and the backward part alone are captured separately under data parallelism
+    _check_lanes(sp.prog.steps[:sp.n_fwd])
+    _check_lanes(sp.prog.steps[sp.n_fwd:])
+    assert sp.prog.launches() > 50
+
+
+def test_training_program_structure(E):
+    cfg, P, sp = _build(E, 'phiseg', 'train')
+    steps = sp.prog.steps
+    names = [s[2] for s in steps]
+    # one fill per arena chunk in front of everything clears all fused-statistics buffers
+    assert names[0] == 'phs_fill_f32' and sp.n_fwd > 1
+    fused = [s for s in steps if s[2] == 'phs_conv2d_stats_acc']
+    assert len(fused) > 80 and 'phs_conv2d_stats' not in names
+    fills = [s for s in steps[:4] if s[2] == 'phs_fill_f32']
+    lo = min(s[1][0] for s in fills)
+    hi = max(s[1][0] + 4 * s[1][1] for s in fills)
+    for s in fused:                     # every statistics buffer lies inside the cleared arena
+        assert lo <= s[1][5] < hi
+    # one filter gradient per live convolution, each into its own slot of the flat gradient buffer, on a wgrad lane
+    wg = [s for s in steps if s[2] == 'phs_conv2d_wgrad']
+    live_w = [n for n, (off, shape, kind) in P.table.items() if kind == 'W' and '_ups_to_' not in n or
+              (kind == 'W' and '_ups_to_' in n and n.split('_ups_to_')[0][-1] == n.split('_ups_to_')[1][0])]
+    assert len(wg) == len(live_w) == 131
+    g0, g1 = P.g.data_ptr(), P.g.data_ptr() + 4 * P.n
+    direct = [s[1][2] for s in wg if g0 <= s[1][2] < g1]
+    assert len(set(direct)) == len(direct) >= 129        # the two im2col'ed input convs go through a scratch + axpy
+    want = {P.ptr(n, 'g') for n in live_w}
+    assert set(direct) <= want
+    assert all(getattr(s, 'lane', 0) >= 3 for s in wg)
+    # forward convolutions: one per live conv (+ none for the dead z*_ups_to_* branches)
+    fwd_convs = [s for s in steps[:sp.n_fwd] if s[2] in ('phs_conv2d', 'phs_conv2d_stats_acc')]
+    assert len(fwd_convs) == 131
+
+
+def test_algorithmic_flops_match_the_survey(E):
+    """25.03 GFLOP / image forward for phiseg_7_5 at 128x128, 22.04 for the Probabilistic U-Net."""
+    cfg, P, sp = _build(E, 'phiseg', 'eval', size=128, B=1)
+    assert abs(sp.conv_flop_fwd / 1e9 - 25.03) < 0.05
+    cfg, P, sp = _build(E, 'probunet', 'eval', size=128, B=1)
+    assert abs(sp.conv_flop_fwd / 1e9 - 22.04) < 0.05
