@@ -227,6 +227,8 @@ def test_pool_upsample_fwd_bwd(call, oracle, shape):
     close(pd, po, what='avgpool fwd')
     call('phs_avgpool2_bwd', call.T(cu(gp, torch.float32)), call.T(gxd), 0)
     close(gxd, x.grad, what='avgpool bwd')
+    call('phs_avgpool2_bwd', call.T(cu(gp, torch.float32)), call.T(gxd), 1)
+    close(gxd, 2 * x.grad, what='avgpool bwd (accumulate)')
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -267,6 +269,34 @@ def test_latent_fwd_bwd(call, oracle, N, hw, zd, gap):
          gap, w / N, *outs)
     for o, ref, nm in zip(outs, (mu_q, sp_q, mu_p, sp_p), ('dmu_q', 'dsp_q', 'dmu_p', 'dsp_p')):
         close(o, ref.grad.reshape(-1), rtol=2e-4, what=nm)
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 24, 64), (1, 16, 16, 192), (3, 4, 6, 32)])
+def test_pool_upsample_bf16_vectors(call, oracle, shape):
+    """The engine's fast mode runs these kernels on bf16 tensors with 8-channel (16-byte) vectors and multiply-high index
+    arithmetic: non-square sizes, three vectors per pixel, several samples."""
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    N, H, W, C = shape
+    xb = torch.randn(shape, generator=g).to(torch.bfloat16)
+    x = xb.double().requires_grad_(True)
+    up = oracle.bilinear_upsample2d(x)
+    gub = torch.randn(up.shape, generator=g).to(torch.bfloat16)
+    up.backward(gub.double())
+    ud = torch.empty(N, 2 * H, 2 * W, C, device='cuda', dtype=torch.bfloat16)
+    call('phs_upsample2_fwd', call.T(xb.cuda()), call.T(ud))
+    close(ud, up, rtol=2 ** -8, atol=2 ** -8, what='upsample fwd bf16')
+    gxd = torch.empty(shape, device='cuda', dtype=torch.bfloat16)
+    call('phs_upsample2_bwd', call.T(gub.cuda()), call.T(gxd), 0)
+    close(gxd, x.grad, rtol=2 ** -7, atol=2 ** -6, what='upsample bwd bf16')
+    x.grad = None
+    po = oracle.averagepool2d(x)
+    gpb = torch.randn(po.shape, generator=g).to(torch.bfloat16)
+    po.backward(gpb.double())
+    pd = torch.empty(N, H // 2, W // 2, C, device='cuda', dtype=torch.bfloat16)
+    call('phs_avgpool2_fwd', call.T(xb.cuda()), call.T(pd))
+    close(pd, po, rtol=2 ** -8, atol=2 ** -8, what='avgpool fwd bf16')
+    call('phs_avgpool2_bwd', call.T(gpb.cuda()), call.T(gxd), 0)
+    close(gxd, x.grad, rtol=2 ** -8, atol=2 ** -8, what='avgpool bwd bf16')
 
 
 # ---------------------------------------------------------------------------------------------------------
