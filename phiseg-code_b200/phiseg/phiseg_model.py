@@ -423,6 +423,47 @@ class phiseg():
             return [np.stack([o[l] for o in outs]) for l in range(len(outs[0]))]
         return np.stack(outs)
 
+    def checks(self):
+        """phiseg_model.py:160-164: a no-op in the reference too (its only check is commented out)."""
+        pass
+
+    def generate_all_output_levels(self, x_in):
+        """phiseg_model.py:498-502: s_out_list of one prior sample with training=False - the per-level head outputs,
+        nearest-neighbour resized to the image size (likelihoods.py:221)."""
+        return self.predict_segmentation_sample_levels(x_in, return_softmax=False)
+
+    def _sample_logits(self, x_in, softmax=False):
+        """One evaluation of s_out_eval (summed level logits) or s_out_eval_sm of a prior sample: [B,H,W,nlabels]."""
+        B = int(np.shape(x_in)[0])
+        sp = self._program('sample', B)
+        self._stage_x(sp, x_in)
+        self._sample_once(sp)
+        return self._np(sp.s_out_sm if softmax else sp.s_out)
+
+    def predict_segmentation_sample_variance_sm_cov(self, x_in, num_samples):
+        """phiseg_model.py:378-403: per-pixel sum of the eigenvalues of the sample covariance of s_out_eval (all classes
+        but the last, clipped to [1e-5, 1-1e-5]); like the reference it expects a single image (np.squeeze)."""
+        segms = [self._sample_logits(x_in) for _ in range(num_samples)]
+        segm_arr = np.squeeze(np.asarray(segms))          # num_samples x H x W x nlabels
+        segm_arr = segm_arr[..., :-1]
+        segm_arr = segm_arr.transpose((1, 2, 3, 0))
+        segm_arr = np.clip(segm_arr, 1e-5, 1 - (1e-5))
+        corr_mat = np.einsum('ghij,ghkj->ghik', segm_arr, segm_arr) / num_samples
+        mu_mat = np.mean(segm_arr, axis=-1)
+        outer_mu = np.einsum('ghi,ghj->ghij', mu_mat, mu_mat)
+        cov_mat = corr_mat - outer_mu
+        eig, _ = np.linalg.eig(cov_mat)
+        return np.sum(eig, axis=-1)
+
+    def predict_segmentation_sample_variance_sm_cov_bf(self, x_in, num_samples):
+        """phiseg_model.py:406-430: per-pixel determinant of np.cov of the softmax samples (the reference loops over the
+        pixels; the batched form below computes the same unbiased covariance and determinant)."""
+        segms = [self._sample_logits(x_in, softmax=True) for _ in range(num_samples)]
+        segm_arr = np.squeeze(np.asarray(segms)).transpose((1, 2, 3, 0)).astype(np.float64)   # H, W, nlabels, samples
+        xc = segm_arr - segm_arr.mean(axis=-1, keepdims=True)
+        cov = np.einsum('ghis,ghjs->ghij', xc, xc) / max(num_samples - 1, 1)
+        return np.linalg.det(cov)
+
     def get_crossentropy_error_map(self, s_gt, x_in, num_samples=100):
         """phiseg_model.py:433-446: mean over samples of the per-pixel cross entropy of s_out_eval."""
         s = np.asarray(s_gt).astype(np.int64)

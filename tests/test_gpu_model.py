@@ -226,6 +226,14 @@ def test_predict_api_and_cuda_graph_replay(pkg, oracle):
     assert smp.shape == (2, B, SIZE, SIZE, 2)
     lv = model_g.generate_samples_from_prior(x, output_all_levels=True)
     assert len(lv) == 5 and lv[4].shape == (B, SIZE, SIZE, 2)
+    # the rest of the reference's class surface (phiseg_model.py:160,378-430,498-502)
+    model_g.checks()
+    lv2 = model_g.generate_all_output_levels(x)
+    assert len(lv2) == 5 and all(a.shape == (B, SIZE, SIZE, 2) for a in lv2)
+    var = model_g.predict_segmentation_sample_variance_sm_cov(x[:1], 4)
+    assert var.shape == (SIZE, SIZE) and np.all(np.isfinite(var))
+    det = model_g.predict_segmentation_sample_variance_sm_cov_bf(x[:1], 4)
+    assert det.shape == (SIZE, SIZE) and np.all(np.isfinite(det)) and np.all(det > -1e-6)
     with pytest.raises(ValueError):
         model_g.training_step(x[:, :32], s, lr=1e-3)
     with pytest.raises(ValueError):

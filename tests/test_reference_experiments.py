@@ -1,0 +1,73 @@
+"""Drop-in check of the config API against the reference's own experiment files: the UNMODIFIED
+files under /root/reference/phiseg/experiments are loaded through experiments.load_experiment (TensorFlow and the
+reference packages resolve to this package's selector modules) and compared attribute by attribute with the shipped
+modules of the same name, and with the network configuration the model derives from them.  Runs only where the reference
+checkout exists (this container); it is not needed, and skipped, on the GPU box."""
+import importlib
+import os
+
+import pytest
+
+REF = '/root/reference/phiseg/experiments'
+NAMES = ['phiseg_7_5', 'phiseg_7_1', 'probunet', 'phiseg_7_5_1annot', 'phiseg_7_1_1annot', 'probunet_1annot']
+
+
+def _public(mod):
+    out = {}
+    for k, v in vars(mod).items():
+        if k.startswith('_') or isinstance(v, type(os)) or k in ('configure',):
+            continue
+        out[k] = v
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not present')
+@pytest.mark.parametrize('name', NAMES)
+def test_unmodified_reference_experiment_loads_and_matches(pkg, name):
+    ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
+    pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
+    ref = ex.load_experiment(os.path.join(REF, name + '.py'))
+    mine = ex.load_experiment(ex.experiment_path(name))
+    a, b = _public(ref), _public(mine)
+    # every attribute the reference file defines exists here with the same value (callables: the same selector symbol)
+    for k, v in a.items():
+        assert k in b, '%s: attribute %s of the reference experiment is missing' % (name, k)
+        w = b[k]
+        if callable(v) or callable(w):
+            assert getattr(v, '__name__', v) == getattr(w, '__name__', w), (name, k, v, w)
+        elif isinstance(v, range):
+            assert list(v) == list(w), (name, k)
+        else:
+            assert v == w, (name, k, v, w)
+    # and the engine derives the same network from both
+    ca, cb = pm.net_config_from_experiment(ref, 'fast'), pm.net_config_from_experiment(mine, 'fast')
+    for f in ('arch', 'H', 'W', 'Cx', 'nlabels', 'zdim0', 'n0', 'R', 'L', 'norm', 'KL_weight', 'xent_weight',
+              'exponential_weighting', 'weight_decay', 'optimizer'):
+        assert getattr(ca, f) == getattr(cb, f), (name, f, getattr(ca, f), getattr(cb, f))
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/phiseg/phiseg_model.py'), reason='reference checkout not present')
+def test_class_surface_covers_the_reference(pkg):
+    """Every public method of the reference's phiseg class (phiseg/phiseg_model.py, read with ast: TensorFlow is not
+    importable) exists on the replacement with the same leading argument names; extra keyword arguments are allowed."""
+    import ast
+    import inspect
+    pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
+    tree = ast.parse(open('/root/reference/phiseg/phiseg_model.py').read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'phiseg'][0]
+    # loss-graph builders are internal to the TF graph construction (their arithmetic lives in the kernels here)
+    internal = {'KL_two_gauss_with_diag_cov', 'multinoulli_loss_with_logits', 'add_residual_multinoulli_loss',
+                'add_hierarchical_KL_div_loss', 'add_weight_decay'}
+    missing, mismatched = [], []
+    for fn in cls.body:
+        if not isinstance(fn, ast.FunctionDef) or fn.name.startswith('_') or fn.name in internal:
+            continue
+        if not hasattr(pm.phiseg, fn.name):
+            missing.append(fn.name)
+            continue
+        ref_args = [a.arg for a in fn.args.args][1:]
+        mine = [p for p in inspect.signature(getattr(pm.phiseg, fn.name)).parameters][1:]
+        if mine[:len(ref_args)] != ref_args:
+            mismatched.append((fn.name, ref_args, mine))
+    assert not missing, 'reference methods without a counterpart: %s' % missing
+    assert not mismatched, 'argument names differ: %s' % mismatched
