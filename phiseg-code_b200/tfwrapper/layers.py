@@ -68,7 +68,7 @@ def global_averagepool2D(x, name=None):
     return stats.view(N, C, 2)[..., 0] / float(H * W)
 
 
-def bilinear_upsample2D(x, name=None, factor=2):
+def bilinear_upsample2D(x, name, factor):
     """tf.image.resize_images(x, [factor*H, factor*W]) = legacy bilinear, align_corners=False (factor 2)."""
     x = _check(x, 'bilinear_upsample2D')
     if factor != 2:

@@ -85,7 +85,7 @@ def test_resampling_ops_and_errors(tfw, oracle):
     assert float((layers.averagepool2D(xd).cpu() - oracle.averagepool2d(x)).abs().max()) < 1e-6
     assert float((layers.bilinear_upsample2D(xd, 'up', 2).cpu() - oracle.bilinear_upsample2d(x)).abs().max()) < 1e-6
     assert float((layers.global_averagepool2D(xd).cpu() - x.mean(dim=(1, 2))).abs().max()) < 1e-5
-    cc = layers.crop_and_concat([xd, layers.bilinear_upsample2D(xd)[:, :8, :12]], axis=-1)
+    cc = layers.crop_and_concat([xd, layers.bilinear_upsample2D(xd, 'up', 2)[:, :8, :12]], axis=-1)
     assert tuple(cc.shape) == (2, 6, 10, 16)
     with pytest.raises(ValueError):
         layers.conv2D(xd, 'bad', strides=(2, 2))
@@ -96,4 +96,8 @@ def test_resampling_ops_and_errors(tfw, oracle):
     with pytest.raises(TypeError):
         norm.batch_norm(xd)                         # `training` is required, as in the reference signature
     with pytest.raises(ValueError):
-        utils.get_weight_variable([3, 3, 1, 1], name='w2', type='xavier_uniform')
+        utils.get_weight_variable([3, 3, 1, 1], name='w2', type='no_such_initialiser')
+    wx = utils.get_weight_variable([3, 3, 4, 8], name='wx')          # the reference's default: xavier_uniform
+    assert float(wx.abs().max()) <= np.sqrt(6.0 / (36 + 72)) + 1e-6 and wx is utils.get_weight_variable([3, 3, 4, 8], name='wx')
+    wp = utils.get_weight_variable([1, 1, 2, 2], name='wp', init_weights=np.arange(4.0))
+    assert wp.flatten().tolist() == [0.0, 1.0, 2.0, 3.0]

@@ -71,3 +71,40 @@ def test_class_surface_covers_the_reference(pkg):
             mismatched.append((fn.name, ref_args, mine))
     assert not missing, 'reference methods without a counterpart: %s' % missing
     assert not mismatched, 'argument names differ: %s' % mismatched
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/tfwrapper/layers.py'), reason='reference checkout not present')
+def test_operator_layer_signatures_match_the_reference(pkg):
+    """The op-level drop-in keeps the reference's argument names, order and defaults (read with ast)."""
+    import ast
+    import inspect
+
+    def ref_sigs(path):
+        tree = ast.parse(open(path).read())
+        out = {}
+        for fn in tree.body:
+            if isinstance(fn, ast.FunctionDef):
+                args = [a.arg for a in fn.args.args]
+                defaults = [ast.literal_eval(d) if isinstance(d, (ast.Constant, ast.Tuple, ast.UnaryOp)) else '<expr>'
+                            for d in fn.args.defaults]
+                out[fn.name] = (args, defaults, fn.args.kwarg.arg if fn.args.kwarg else None)
+        return out
+
+    layers = importlib.import_module('phiseg_code_b200.tfwrapper.layers')
+    utils = importlib.import_module('phiseg_code_b200.tfwrapper.utils')
+    checks = [(ref_sigs('/root/reference/tfwrapper/layers.py'), layers,
+               ['conv2D', 'averagepool2D', 'global_averagepool2D', 'bilinear_upsample2D', 'crop_and_concat']),
+              (ref_sigs('/root/reference/tfwrapper/utils.py'), utils, ['get_weight_variable', 'get_bias_variable'])]
+    for ref, mod, names in checks:
+        for n in names:
+            args, defaults, kwarg = ref[n]
+            sig = inspect.signature(getattr(mod, n))
+            mine = [p for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+            assert [p.name for p in mine] == args, (n, args, [p.name for p in mine])
+            mine_def = [p.default for p in mine if p.default is not inspect.Parameter.empty]
+            assert len(mine_def) == len(defaults), (n, defaults, mine_def)
+            for d_ref, d_mine in zip(defaults, mine_def):
+                if d_ref != '<expr>':
+                    assert d_ref == d_mine, (n, d_ref, d_mine)
+            has_kw = any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())
+            assert has_kw == (kwarg is not None), (n, kwarg)
