@@ -101,3 +101,24 @@ def test_algorithmic_flops_match_the_survey(E):
     assert abs(sp.conv_flop_fwd / 1e9 - 25.03) < 0.05
     cfg, P, sp = _build(E, 'probunet', 'eval', size=128, B=1)
     assert abs(sp.conv_flop_fwd / 1e9 - 22.04) < 0.05
+
+
+@pytest.mark.parametrize('arch,norm', [('phiseg', 'batch_norm'), ('phiseg', 'group_norm'), ('probunet', 'batch_norm'),
+                                       ('probunet', 'group_norm')])
+def test_variable_set_matches_the_oracle(E, oracle, arch, norm):
+    """Same TF variable names and shapes in the engine's flat parameter buffer and in the oracle's parameter dict
+    (checkpoints and set_weights / get_weights rely on it), and the SURVEY's parameter count for phiseg_7_5."""
+    kw = dict(arch=arch, image_size=(128, 128, 1), mode='parity', norm=norm)
+    if arch == 'probunet':
+        kw.update(zdim0=6, latent_levels=1)
+    cfg = E.NetConfig(**kw)
+    spec = {n: tuple(shape) for n, shape, kind in E.build_spec(cfg)}
+    okw = dict(zdim0=6, latent_levels=1) if arch == 'probunet' else {}
+    orc = oracle.Oracle(arch, image_size=(128, 128, 1), norm=norm, **okw)
+    P = orc.init_params(seed=1)
+    assert set(spec) == set(P), sorted(set(spec) ^ set(P))[:8]
+    for n, shape in spec.items():
+        assert tuple(P[n].shape) == shape, (n, shape, tuple(P[n].shape))
+    if arch == 'phiseg' and norm == 'batch_norm':
+        n_w = sum(int(torch.tensor(s).prod()) for n, s in spec.items() if n.endswith('/W'))
+        assert abs(n_w / 1e6 - 18.68) < 0.1          # conv weights incl. the dead z*_ups_to_* branches (SURVEY 8d)
