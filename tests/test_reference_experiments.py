@@ -108,3 +108,38 @@ def test_operator_layer_signatures_match_the_reference(pkg):
                     assert d_ref == d_mine, (n, d_ref, d_mine)
             has_kw = any(p.kind == p.VAR_KEYWORD for p in sig.parameters.values())
             assert has_kw == (kwarg is not None), (n, kwarg)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/phiseg/model_zoo'), reason='reference checkout not present')
+def test_variable_names_follow_the_reference_scopes(pkg):
+    """Every convolution scope name in the flat parameter buffer (engine.build_spec) matches a name / name pattern the
+    reference's model_zoo passes to layers.conv2D or tf.variable_scope (string literals and '...%d...' % (...) format
+    strings, read with ast), under the top-level scopes posterior / prior / likelihood."""
+    import ast
+    import re
+    eng = importlib.import_module('phiseg_code_b200.engine')
+    patterns = set()
+    for f in ('posteriors.py', 'priors.py', 'likelihoods.py'):
+        tree = ast.parse(open(os.path.join('/root/reference/phiseg/model_zoo', f)).read())
+        for node in ast.walk(tree):
+            s = None
+            if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Mod) and isinstance(node.left, ast.Constant) \
+                    and isinstance(node.left.value, str):
+                s = node.left.value
+            elif isinstance(node, ast.Constant) and isinstance(node.value, str):
+                s = node.value
+            if s and re.fullmatch(r'[A-Za-z0-9_%]+', s):
+                patterns.add(s)
+    regs = [re.compile('^' + re.escape(p).replace('%d', r'\d+') + '$') for p in patterns]
+
+    def known(part):
+        return any(r.match(part) for r in regs)
+
+    norm_tail = {'batch_norm', 'BatchNorm', 'group_norm', 'W', 'b', 'beta', 'gamma', 'moving_mean', 'moving_variance'}
+    for arch, kw in (('phiseg', {}), ('probunet', dict(zdim0=6, latent_levels=1))):
+        cfg = eng.NetConfig(arch=arch, image_size=(128, 128, 1), mode='parity', norm='batch_norm', **kw)
+        for name, shape, kind in eng.build_spec(cfg):
+            parts = name.split('/')
+            assert parts[0] in ('posterior', 'prior', 'likelihood'), name
+            for part in parts[1:]:
+                assert part in norm_tail or known(part), 'scope %r of %s has no counterpart in the reference' % (part, name)
