@@ -3,7 +3,20 @@ Each experiment module calls configure(...) with what it overrides and publishes
 which is the config API phiseg_model.phiseg reads."""
 
 
-def configure(experiment_name, **over):
+def _selectors(nets, norm, optimizer):
+    """The symbols an experiment assigns to posterior / prior / likelihood / layer_norm / optimizer."""
+    from ..model_zoo import likelihoods, posteriors, priors
+    from ...tfwrapper import normalisation as tfnorm
+    from ... import tf_compat
+    net = {'phiseg': (posteriors.phiseg, priors.phiseg, likelihoods.phiseg),
+           'prob_unet2D': (posteriors.prob_unet2D, priors.prob_unet2D, likelihoods.prob_unet2D),
+           'det_unet2D': (posteriors.dummy, priors.dummy, likelihoods.det_unet2D)}[nets]
+    return dict(posterior=net[0], prior=net[1], likelihood=net[2],
+                layer_norm={'batch_norm': tfnorm.batch_norm, 'group_norm2D': tfnorm.group_norm2D}[norm],
+                optimizer={'adam': tf_compat.train.AdamOptimizer, 'momentum': tf_compat.train.MomentumOptimizer}[optimizer])
+
+
+def configure(experiment_name, nets='phiseg', norm='batch_norm', optimizer='adam', **over):
     nlabels = over.get('nlabels', 2)
     num_labels_per_subject = over.get('num_labels_per_subject', 4)
     cfg = dict(
@@ -35,5 +48,6 @@ def configure(experiment_name, **over):
         num_validation_images=100,
         tensorboard_update_frequency=100,
     )
+    cfg.update(_selectors(nets, norm, optimizer))
     cfg.update(over)
     return cfg
