@@ -122,3 +122,21 @@ def test_variable_set_matches_the_oracle(E, oracle, arch, norm):
     if arch == 'phiseg' and norm == 'batch_norm':
         n_w = sum(int(torch.tensor(s).prod()) for n, s in spec.items() if n.endswith('/W'))
         assert abs(n_w / 1e6 - 18.68) < 0.1          # conv weights incl. the dead z*_ups_to_* branches
+
+
+def test_latest_checkpoint_resolution(pkg, tmp_path):
+    """Counterpart of tfwrapper/utils.py:189-210 (get_latest_model_checkpoint_path): the highest iteration with the
+    given prefix wins; other prefixes and files are ignored; no checkpoint -> None."""
+    pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
+    assert pm._latest_checkpoint(str(tmp_path), 'model.ckpt') is None
+    assert pm._latest_checkpoint(str(tmp_path / 'missing'), 'model.ckpt') is None
+    for f in ('model.ckpt-500.npz', 'model.ckpt-12000.npz', 'model.ckpt-9000.npz', 'model_best_loss.ckpt-99999.npz',
+              'model.ckpt-13000.txt', 'notes.npz'):
+        (tmp_path / f).write_bytes(b'')
+    assert pm._latest_checkpoint(str(tmp_path), 'model.ckpt').endswith('model.ckpt-12000.npz')
+    assert pm._latest_checkpoint(str(tmp_path), 'model_best_loss.ckpt').endswith('model_best_loss.ckpt-99999.npz')
+    assert pm._latest_checkpoint(str(tmp_path), 'model_best_ged.ckpt') is None
+    # learning-rate schedule lookup (phiseg_model.py:189-190, utils.find_floor_in_list)
+    assert pm.find_floor_in_list([0, 1000, 5000], 999) == 0
+    assert pm.find_floor_in_list([0, 1000, 5000], 1000) == 1000
+    assert pm.find_floor_in_list([5000, 0, 1000], 7000) == 5000
