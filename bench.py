@@ -162,7 +162,7 @@ def main():
 
     import numpy as np
     import torch
-    from __graft_entry__ import load_package, load_oracle
+    from __graft_entry__ import load_package
     load_package()
     import importlib
     parallel = importlib.import_module('phiseg_code_b200.parallel')
@@ -174,8 +174,8 @@ def main():
 
     exp = ex.load_experiment(ex.experiment_path(exp_name))
     model = pm.phiseg(exp, mode=args.mode, use_cuda_graph=not args.no_graph)
-    o = load_oracle()   # only its synthetic-input generator and (rank 0) the cpu_baseline leg are used here
-    x, s = o.synthetic_batch(batch, size, size, nlabels, seed=1235 + rank)
+    data = importlib.import_module('phiseg_code_b200.data')     # the oracle is only touched by the cpu_baseline leg
+    x, s = data.synthetic_batch(batch, size, size, nlabels, seed=1235 + rank)
     lr = 1e-3
 
     # ---- device-resident throughput ---------------------------------------------------------------------

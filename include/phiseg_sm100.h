@@ -48,15 +48,18 @@ int phs_device_ok(void);
 int phs_conv2d(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
                int accumulate, int impl, void* stream);
 /* forward convolution (tensor-core path only) that also accumulates, from the fp32 accumulators, the per-(sample,
- * channel) sum and sum of squares the following batch_norm / group_norm2D needs: stats[N][C][2] must be zeroed. */
+ * channel) sum and sum of squares the following batch_norm / group_norm2D needs: stats[N][C][2] must be zeroed.
+ * Every statistics / reduction buffer of this library (stats, sums) is DOUBLE: the kernels add fp32 partial sums into
+ * them with fp64 atomics, whose result does not depend on the arrival order in practice, so a step is reproducible
+ * run to run (fp32 atomics were not, and bf16 roundings downstream amplified the difference). */
 int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
-                     float* stats, void* stream);
+                     double* stats, void* stream);
 /* Same, for callers that clear the statistics of MANY layers with one fill (the launch-program engine keeps them in one
  * arena): adds onto stats, which the caller must have zeroed, and launches no memset of its own.  stats holds
- * (N + 1) * C * 2 floats here: the per-sample sums [N][C][2] followed by the batch totals [C][2] that batch norm needs
+ * (N + 1) * C * 2 doubles here: the per-sample sums [N][C][2] followed by the batch totals [C][2] that batch norm needs
  * (phs_norm_act_fwd_stats reads them). */
 int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
-                         float* stats, void* stream);
+                         double* stats, void* stream);
 /* Host-only introspection (no device work, callable without a GPU): the launch geometry the halo-tile tcgen05 kernel
  * would use for a 3x3 layer.  plan[12] = {CTAs per SM, S, halo stages, filter stages, filter resident, staging group,
  * accumulator stages, TMEM columns, dynamic shared memory bytes, grid, tiles, BK}; accumulate bit 1 = statistics buffer
@@ -73,15 +76,15 @@ int phs_conv2d_wgrad(const phs_tensor* x, const phs_tensor* dy, float* dw, float
 
 /* ---- normalisation + activation -------------------------------------------------------------------------- */
 /* per-(sample,channel) sum and sum of squares of y: stats[N][C][2] (overwritten). */
-int phs_chan_stats(const phs_tensor* y, float* stats, void* stream);
+int phs_chan_stats(const phs_tensor* y, double* stats, void* stream);
 /* stats -> mean[N][C], rstd[N][C] for batch_norm (train: batch statistics + moving-average update with decay,
  * Bessel-corrected variance; infer: moving statistics) or group_norm2D (groups of C/max(2,C/16) channels). */
-int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
+int phs_norm_finalize(const double* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
                       float* moving_var, float* mean, float* rstd, void* stream);
 /* phs_norm_finalize + phs_norm_act_fwd in one launch, for training-mode batch_norm and for group_norm2D: mean / rstd are
- * derived inside the kernel from the phs_conv2d_stats_acc layout ((N + 1) * C * 2 floats), written to mean/rstd[N][C] for
+ * derived inside the kernel from the phs_conv2d_stats_acc layout ((N + 1) * C * 2 doubles), written to mean/rstd[N][C] for
  * the backward kernels, and the batch-norm moving averages are updated (decay; may be NULL for group norm). */
-int phs_norm_act_fwd_stats(const phs_tensor* y, const float* stats, int mode, float eps, float decay, float* moving_mean,
+int phs_norm_act_fwd_stats(const phs_tensor* y, const double* stats, int mode, float eps, float decay, float* moving_mean,
                            float* moving_var, float* mean, float* rstd, const float* gamma, const float* beta, int relu,
                            const phs_tensor* a, void* stream);
 /* a = act(gamma*(y-mean)*rstd + beta); relu != 0 applies tf.nn.relu (tfwrapper/layers.py:134-135). */
@@ -89,16 +92,16 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
                      int relu, const phs_tensor* a, void* stream);
 /* backward of the above, three launches: sums[N][C][2] = (sum g*mask, sum g*mask*xhat) ... */
 int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                        const float* gamma, const float* beta, int relu, float* sums, void* stream);
+                        const float* gamma, const float* beta, int relu, double* sums, void* stream);
 /* batch_norm (training) only: phs_norm_bwd_reduce with phs_norm_bwd_finalize folded into its last block.  sums[N][C][2]
  * and *counter must have been zeroed by the caller (the engine clears one arena per step); writes coef[N][C][2] and
  * (+)= dgamma / dbeta.  The convolution in front of a batch norm has no bias, so there is no dbias. */
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, int relu, float* sums, unsigned int* counter,
+                           const float* gamma, const float* beta, int relu, double* sums, unsigned int* counter,
                            float* coef, float* dgamma, float* dbeta, int accumulate, void* stream);
 /* ... dgamma/dbeta (+= when accumulate) and per-(n,c) coefficients coef[N][C][2]; dbias (may be NULL) is the
  * gradient of the conv bias that precedes the norm, derived analytically from the forward statistics ... */
-int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* mean, const float* rstd,
+int phs_norm_bwd_finalize(const double* sums, const double* stats, const float* mean, const float* rstd,
                           const float* gamma, int N, int HW, int C, int mode, float* coef, float* dgamma, float* dbeta,
                           float* dbias, int accumulate, void* stream);
 /* ... dy = rstd*(g*mask*gamma - m1 - xhat*m2). */
@@ -168,6 +171,12 @@ int phs_fill_f32(float* p, int64_t n, float v, void* stream);
 int phs_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream);
 /* out[0] += scale * sum(src^2): the tf.nn.l2_loss terms of add_weight_decay (phiseg_model.py:290-300) */
 int phs_sumsq_f32(const float* src, int64_t n, float scale, float* out, void* stream);
+/* add_weight_decay (phiseg_model.py:290-300: weight_decay_weight * sum over the 'weight_variables' collection of
+ * tf.nn.l2_loss) over all filters in one launch.  segs[nseg][2] (device) = (offset, count) of each filter inside the flat
+ * fp32 parameter buffer; loss_out[0] += 0.5 * wd * sum W^2 (may be NULL); grads (same layout as params; may be NULL, e.g.
+ * for validation losses) += wd * W. */
+int phs_weight_decay(const float* params, float* grads, const int64_t* segs, int nseg, float wd, float* loss_out,
+                     void* stream);
 /* first-maximum argmax over the label axis of [npix, nlabels] (np.argmax in predict, phiseg_model.py:351-353) */
 int phs_argmax_f32(const float* src, int64_t npix, int nlabels, int64_t* out, void* stream);
 

@@ -28,7 +28,7 @@ int conv2d_simt(const phs_tensor* x, const float* w, const float* bias, const ph
 int conv2d_wgrad_simt(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,
                       cudaStream_t st);
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
-              int accumulate, float* stats, cudaStream_t st);
+              int accumulate, double* stats, cudaStream_t st);
 int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float* db, int ksize, int accumulate,
                     cudaStream_t st);
 
@@ -68,7 +68,7 @@ int phs_conv2d(const phs_tensor* x, const void* w, const float* bias, const phs_
 }
 
 int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
-                     float* stats, void* stream) {
+                     double* stats, void* stream) {
   int rc = check_conv_args("phs_conv2d_stats", x, w, y, ksize);
   if (rc) return rc;
   PHS_REQUIRE(stats, "phs_conv2d_stats: null stats");
@@ -76,7 +76,7 @@ int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, cons
 }
 
 int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
-                         float* stats, void* stream) {
+                         double* stats, void* stream) {
   int rc = check_conv_args("phs_conv2d_stats_acc", x, w, y, ksize);
   if (rc) return rc;
   PHS_REQUIRE(stats, "phs_conv2d_stats_acc: null stats");

@@ -43,8 +43,8 @@ struct HaloParams {
   int y_ld, y_f32;
   const float* bias;
   int accumulate;
-  float* stats;               // [N][Cout][2] or null
-  float* totals;              // [Cout][2] batch totals (phs_conv2d_stats_acc layout) or null
+  double* stats;              // [N][Cout][2] or null (fp64: see flush())
+  double* totals;             // [Cout][2] batch totals (phs_conv2d_stats_acc layout) or null
   int stage_g;                // 0: direct register -> global stores; 32 | 64: channels per smem-staged TMA store group
   long long* trace;           // PHS_HALO_TRACE: per-role clock64 stamps of the first CTAs (tools/trace_halo.py)
   int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
@@ -270,13 +270,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int st_n = -1;
     auto flush = [&]() {
       if (p.stats && st_n >= 0) {
-        float* dst = p.stats + (size_t)st_n * p.Cout * 2;
+        // fp64 accumulators: the partials are fp32 (24-bit) values of similar magnitude, so their fp64 sum is exact in
+        // (almost) any order - the statistics, and with them every bf16 rounding downstream, do not depend on the order in
+        // which the CTAs arrive (fp32 atomics made the whole forward pass irreproducible run to run)
+        double* dst = p.stats + (size_t)st_n * p.Cout * 2;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j * 16 < p.Cout) {
             const int c = j * 16 + col16(lane);
-            atomicAdd(dst + c * 2 + (lane & 1), (lane & 1) ? st_q[j] : st_s[j]);
-            if (p.totals) atomicAdd(p.totals + c * 2 + (lane & 1), (lane & 1) ? st_q[j] : st_s[j]);
+            const double v = (double)((lane & 1) ? st_q[j] : st_s[j]);
+            atomicAdd(dst + c * 2 + (lane & 1), v);
+            if (p.totals) atomicAdd(p.totals + c * 2 + (lane & 1), v);
             st_s[j] = st_q[j] = 0.f;
           }
       }
@@ -424,7 +428,7 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
 
 // plan_out != nullptr: only choose the geometry and report it (phs_conv_halo_plan), nothing is launched
 static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
-                          float* stats, cudaStream_t st, int* plan_out) {
+                          double* stats, cudaStream_t st, int* plan_out) {
   const int accumulate = accumulate_flags & 1;
   const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
   const int BK = x->C % 64 == 0 ? 64 : 32;
@@ -555,7 +559,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   if (rc) return rc;
   CUtensorMap tmY = tmA;
   if (p.stage_g && (rc = activation_map(y, p.stage_g, SUB_W, TILE_H, 1, &tmY))) return rc;
-  if (stats && !stats_prezeroed) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)x->N * y->C, st);
+  if (stats && !stats_prezeroed) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)x->N * y->C, st);
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<64>, &attr))) return rc;
@@ -569,7 +573,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
 }
 
 int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
-                float* stats, cudaStream_t st) {
+                double* stats, cudaStream_t st) {
   return conv_halo_impl(x, w, bias, y, accumulate_flags, stats, st, nullptr);
 }
 
@@ -580,7 +584,7 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
 extern "C" int phs_conv_halo_plan(const phs_tensor* x, const phs_tensor* y, int accumulate, int with_stats, int* plan) {
   PHS_REQUIRE(x && y && plan, "phs_conv_halo_plan: null argument");
   if (!conv_halo_eligible(x, y, 3)) return 0;
-  static float dummy_stats;
+  static double dummy_stats;
   int rc = conv_halo_impl(x, nullptr, nullptr, y, accumulate, with_stats ? &dummy_stats : nullptr, nullptr, plan);
   return rc == 0 ? 1 : (rc == -3 ? 0 : rc);
 }

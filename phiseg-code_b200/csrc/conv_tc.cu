@@ -485,14 +485,14 @@ __global__ void __launch_bounds__(256) bias_grad_bf16_kernel(const bf16* __restr
 // dispatch
 // ------------------------------------------------------------------------------------------------------------
 bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize);
-int chan_stats_run(const phs_tensor* y, float* stats, bool with_totals, bool zero_first, cudaStream_t st);
-int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate, float* stats,
+int chan_stats_run(const phs_tensor* y, double* stats, bool with_totals, bool zero_first, cudaStream_t st);
+int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate, double* stats,
                 cudaStream_t st);
 bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
 int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
 
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
-              int accumulate, float* stats, cudaStream_t st) {
+              int accumulate, double* stats, cudaStream_t st) {
   // the gradient w.r.t. the input is the same GEMM on the dgrad filter shadow
   PHS_REQUIRE(x->dtype == PHS_BF16, "conv2d_tc: input must be bf16");
   const int stats_prezeroed = accumulate & 2;   // bit 1: the caller zeroed stats (phs_conv2d_stats_acc)

@@ -27,8 +27,8 @@ struct BwdFin {
 
 template <typename T, int V>
 __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __restrict__ y, int HW, int C, int ld,
-                                                                 int pix_per_block, float* __restrict__ stats,
-                                                                 float* __restrict__ totals) {
+                                                                 int pix_per_block, double* __restrict__ stats,
+                                                                 double* __restrict__ totals) {
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
   for (int i = threadIdx.x; i < C * 2; i += RED_THREADS) {
     float a = 0.f;
     for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
-    atomicAdd(&stats[(size_t)n * C * 2 + i], a);
-    if (totals) atomicAdd(&totals[i], a);
+    atomicAdd(&stats[(size_t)n * C * 2 + i], (double)a);   // fp64: order-independent in practice (conv_halo.cu flush)
+    if (totals) atomicAdd(&totals[i], (double)a);
   }
 }
 
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
     norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                           float* __restrict__ sums, BwdFin fin) {
+                           double* __restrict__ sums, BwdFin fin) {
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
   for (int i = threadIdx.x; i < C * 2; i += RED_THREADS) {
     float a = 0.f;
     for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
-    atomicAdd(&sums[(size_t)n * C * 2 + i], a);
+    atomicAdd(&sums[(size_t)n * C * 2 + i], (double)a);
   }
   if (fin.counter == nullptr) return;
   // fused batch-norm finalize: the block that arrives last sees every block's sums and turns them into the apply
@@ -164,14 +164,14 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
     double a1 = 0.0, a2 = 0.0;
     int nn = 0;
     for (; nn + 8 <= N; nn += 8) {
-      float2 v[8];
+      double2 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const float2*>(sums) + (size_t)(nn + u) * C + c);
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const double2*>(sums) + (size_t)(nn + u) * C + c);
 #pragma unroll
       for (int u = 0; u < 8; ++u) { a1 += v[u].x; a2 += v[u].y; }
     }
     for (; nn < N; ++nn) {
-      const float2 v = __ldcg(reinterpret_cast<const float2*>(sums) + (size_t)nn * C + c);
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(sums) + (size_t)nn * C + c);
       a1 += v.x; a2 += v.y;
     }
     const double cnt = (double)HW * N;
@@ -206,32 +206,32 @@ static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size
 
 // stats[N][C][2] (+)= per-sample sums; with_totals: the [C][2] batch totals that follow them are accumulated too
 // (layout of phs_conv2d_stats_acc); zero_first: clear the per-sample part (the plain phs_chan_stats contract)
-int chan_stats_run(const phs_tensor* y, float* stats, bool with_totals, bool zero_first, cudaStream_t st) {
+int chan_stats_run(const phs_tensor* y, double* stats, bool with_totals, bool zero_first, cudaStream_t st) {
   int HW = y->H * y->W;
-  if (zero_first) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
+  if (zero_first) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)y->N * y->C, st);
   int v = pick_vec(y);
   dim3 grid; int ppb; size_t smem;
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_chan_stats: C=%d too large", y->C);
-  float* totals = with_totals ? stats + (size_t)y->N * y->C * 2 : nullptr;
+  double* totals = with_totals ? stats + (size_t)y->N * y->C * 2 : nullptr;
   PHS_DISPATCH_DTYPE(y->dtype, T, PHS_DISPATCH_VEC(v, V, (chan_stats_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
                                                             (const T*)y->ptr, HW, y->C, y->ld, ppb, stats, totals))));
   return phs_check_launch("chan_stats");
 }
 
-int phs_chan_stats(const phs_tensor* y, float* stats, void* stream) {
+int phs_chan_stats(const phs_tensor* y, double* stats, void* stream) {
   PHS_REQUIRE(y && y->ptr && stats, "phs_chan_stats: null argument");
   return chan_stats_run(y, stats, false, true, (cudaStream_t)stream);
 }
 
 int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                        const float* gamma, const float* beta, int relu, float* sums, void* stream) {
+                        const float* gamma, const float* beta, int relu, double* sums, void* stream) {
   PHS_REQUIRE(g && y && g->ptr && y->ptr && sums, "phs_norm_bwd_reduce: null argument");
   PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C,
               "phs_norm_bwd_reduce: g/y mismatch");
   cudaStream_t st = (cudaStream_t)stream;
   int HW = y->H * y->W;
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)y->N * y->C, st);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)y->N * y->C, st);
   int v = min_vec(pick_vec(y), pick_vec(g));
   dim3 grid; int ppb; size_t smem;
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
@@ -244,7 +244,7 @@ int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* m
 }
 
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, int relu, float* sums, unsigned int* counter,
+                           const float* gamma, const float* beta, int relu, double* sums, unsigned int* counter,
                            float* coef, float* dgamma, float* dbeta, int accumulate, void* stream) {
   PHS_REQUIRE(g && y && g->ptr && y->ptr && sums && counter && coef, "phs_norm_bwd_reduce_bn: null argument");
   PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C,
@@ -268,7 +268,7 @@ int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float
 // ---------------------------------------------------------------------------------------------------------
 // one WARP per channel (BN: lanes stride over the samples) or one thread per (n, c) (GN)
 
-__global__ void __launch_bounds__(128) norm_finalize_kernel(const float* __restrict__ stats, int N, int HW, int C,
+__global__ void __launch_bounds__(128) norm_finalize_kernel(const double* __restrict__ stats, int N, int HW, int C,
                                                             int mode, float eps, float decay, float* moving_mean,
                                                             float* moving_var, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const float* __restr
   }
 }
 
-int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
+int phs_norm_finalize(const double* stats, int N, int HW, int C, int mode, float eps, float decay, float* moving_mean,
                       float* moving_var, float* mean, float* rstd, void* stream) {
   PHS_REQUIRE(mean && rstd, "phs_norm_finalize: null output");
   PHS_REQUIRE(mode == PHS_NORM_BN_INFER || stats, "phs_norm_finalize: stats required");
@@ -344,7 +344,7 @@ int phs_norm_finalize(const float* stats, int N, int HW, int C, int mode, float 
 //   dx = rstd*(g'*gamma - m1 - xhat*m2);   dbias[c] = sum_{n,hw} dx  (closed form from the forward sums)
 // one warp per channel, lanes stride over the samples
 __global__ void __launch_bounds__(128)
-    norm_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
+    norm_bwd_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ stats,
                              const float* __restrict__ mean, const float* __restrict__ rstd,
                              const float* __restrict__ gamma, int N, int HW, int C, int mode, float* __restrict__ coef,
                              float* dgamma, float* dbeta, float* dbias, int accumulate) {
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(128)
     for (int n = lane; n < N; n += 32) {
       double m1 = 0.0, m2 = 0.0;
       for (int i = 0; i < cpg; ++i) {
-        float gi = gamma[c0 + i];
+        double gi = gamma[c0 + i];
         m1 += (double)gi * sums[((size_t)n * C + c0 + i) * 2];
         m2 += (double)gi * sums[((size_t)n * C + c0 + i) * 2 + 1];
       }
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-int phs_norm_bwd_finalize(const float* sums, const float* stats, const float* mean, const float* rstd,
+int phs_norm_bwd_finalize(const double* sums, const double* stats, const float* mean, const float* rstd,
                           const float* gamma, int N, int HW, int C, int mode, float* coef, float* dgamma, float* dbeta,
                           float* dbias, int accumulate, void* stream) {
   PHS_REQUIRE(sums && mean && rstd && gamma && coef, "phs_norm_bwd_finalize: null argument");
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256)
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
     norm_act_fwd_stats_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C,
-                              int pix_per_block, const float* __restrict__ stats, int mode, float eps, float decay,
+                              int pix_per_block, const double* __restrict__ stats, int mode, float eps, float decay,
                               float* moving_mean, float* moving_var, float* __restrict__ mean_out,
                               float* __restrict__ rstd_out, const float* __restrict__ gamma,
                               const float* __restrict__ beta, int relu) {
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(256)
   const int p1 = min(HW, p0 + pix_per_block);
   const T* yb = y + (size_t)n * HW * ldy;
   T* ab = a + (size_t)n * HW * lda;
-  const float* totals = stats + (size_t)N * C * 2;
+  const double* totals = stats + (size_t)N * C * 2;
   const int G = max(2, C / 16), cpg = C / G;
   for (int cv = lane_c; cv < nvec; cv += CW) {
     float sc[V], sh[V];
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256)
         const int grp = c / cpg;
         if (grp != g_cached) {
           double s = 0.0, q = 0.0;
-          const float* gs = stats + ((size_t)n * C + (size_t)grp * cpg) * 2;
+          const double* gs = stats + ((size_t)n * C + (size_t)grp * cpg) * 2;
           for (int i = 0; i < cpg; ++i) { s += gs[2 * i]; q += gs[2 * i + 1]; }
           const double cnt = (double)HW * cpg;
           g_m = s / cnt;
@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(256)
         m = g_m; r = g_r;
       } else {
         const double cnt = (double)HW * N;
-        m = (double)totals[2 * c] / cnt;
-        double var = (double)totals[2 * c + 1] / cnt - m * m;
+        m = totals[2 * c] / cnt;
+        double var = totals[2 * c + 1] / cnt - m * m;
         if (var < 0) var = 0;
         r = 1.0 / sqrt(var + (double)eps);
         if (moving_mean && blockIdx.x == 0 && n == 0 && lane_p == 0) {
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int phs_norm_act_fwd_stats(const phs_tensor* y, const float* stats, int mode, float eps, float decay, float* moving_mean,
+int phs_norm_act_fwd_stats(const phs_tensor* y, const double* stats, int mode, float eps, float decay, float* moving_mean,
                            float* moving_var, float* mean, float* rstd, const float* gamma, const float* beta, int relu,
                            const phs_tensor* a, void* stream) {
   PHS_REQUIRE(y && a && y->ptr && a->ptr && stats && mean && rstd && gamma && beta, "phs_norm_act_fwd_stats: null argument");
@@ -1057,6 +1057,38 @@ int phs_sumsq_f32(const float* src, int64_t n, float scale, float* out, void* st
   if (b > 296) b = 296;
   sumsq_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(src, n, scale, out);
   return phs_check_launch("sumsq");
+}
+
+// add_weight_decay (phiseg_model.py:290-300) for ALL filters in one launch: segs[i] = (offset, count) of filter i in the
+// flat fp32 parameter buffer; out[0] += wd * sum_i l2_loss(W_i) = 0.5 * wd * sum W^2, and (g != null) g += wd * W, the
+// gradient of that term.  grid = (blocks per segment, segments).
+__global__ void __launch_bounds__(256) weight_decay_kernel(const float* __restrict__ p, float* __restrict__ g,
+                                                           const int64_t* __restrict__ segs, float wd, float* out) {
+  const int64_t off = segs[2 * blockIdx.y], n = segs[2 * blockIdx.y + 1];
+  const float* w = p + off;
+  float a = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    a += v * v;
+    if (g) g[off + i] += wd * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0 && out) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    atomicAdd(out, 0.5f * wd * t);
+  }
+}
+int phs_weight_decay(const float* params, float* grads, const int64_t* segs, int nseg, float wd, float* loss_out,
+                     void* stream) {
+  PHS_REQUIRE((params && segs) || nseg == 0, "phs_weight_decay: null");
+  PHS_REQUIRE(nseg >= 0 && nseg <= 65535, "phs_weight_decay: nseg=%d", nseg);
+  if (nseg == 0) return 0;
+  weight_decay_kernel<<<dim3(8, nseg), 256, 0, (cudaStream_t)stream>>>(params, grads, segs, wd, loss_out);
+  return phs_check_launch("weight_decay");
 }
 
 // argmax over the last axis of [npix, nl] (np.argmax of the accumulated softmax in predict, phiseg_model.py:351-353):

@@ -387,9 +387,10 @@ class Program:
         self.steps.append(st)
 
     def stats_vec(self, n):
-        """Fused-statistics buffer of one layer, carved out of an arena that ONE fill at the start of the program clears
-        (a memset node in front of every convolution sat on the critical path ~100 times per step)."""
-        n = (int(n) + 63) // 64 * 64
+        """Fused-statistics buffer of one layer (n DOUBLES: the library accumulates statistics with fp64 atomics so that a
+        step is reproducible run to run), carved out of an arena that ONE fill at the start of the program clears (a
+        memset node in front of every convolution sat on the critical path ~100 times per step)."""
+        n = (2 * int(n) + 63) // 64 * 64          # in float32 units; every carve-out stays 256-byte aligned
         chunk = 1 << 22
         if not hasattr(self, '_arena') or self._arena_off + n > self._arena[-1].numel():
             if not hasattr(self, '_arena'):
@@ -408,11 +409,15 @@ class Program:
         ar = getattr(self, '_arena', [])
         return [(t.data_ptr(), t.numel() if i < len(ar) - 1 else self._arena_off) for i, t in enumerate(ar)]
 
-    def vec(self, n, zero=False):
-        t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=torch.float32, device=self.device)
+    def vec(self, n, zero=False, dtype=torch.float32):
+        t = (torch.zeros if zero else torch.empty)(max(int(n), 1), dtype=dtype, device=self.device)
         self.keep.append(t)
-        self.bytes += 4 * t.numel()
+        self.bytes += t.element_size() * t.numel()
         return t
+
+    def dvec(self, n, zero=False):
+        """float64 vector (statistics / reduction buffers, see stats_vec)"""
+        return self.vec(n, zero, torch.float64)
 
     def run_eager(self, steps=None):
         """Enqueue the launches.  Lane 0 is the current stream; independent sub-graphs (the posterior and prior
@@ -552,7 +557,7 @@ class Builder:
             mode, eps = self._norm_mode()
             N, HW, C = x.N, x.H * x.W, cout
             fused_stats = tc and mode != L.NORM_BN_INFER
-            stats = pr.stats_vec((N + 1) * C * 2) if fused_stats else pr.vec(N * C * 2)
+            stats = pr.stats_vec((N + 1) * C * 2) if fused_stats else pr.dvec(N * C * 2)
             if fused_stats:
                 # statistics of the following norm come out of the conv epilogue (fp32 accumulators); the arena they
                 # live in is cleared by one fill at the start of the program (build_program)
@@ -590,16 +595,16 @@ class Builder:
                 if nb is not None:
                     mode, stats, mean, rstd, gamma, beta, dgamma, dbeta = nb
                     N, HW, C = x.N, x.H * x.W, cout
-                    sums, coef = pr.vec(N * C * 2), pr.vec(N * C * 2)
+                    sums, coef = pr.dvec(N * C * 2), pr.vec(N * C * 2)
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
                     if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_FUSED_BN_BWD'):
                         # reduce + finalize in one launch (sums and the block ticket in the pre-cleared arena).  Measured
                         # neutral-to-slower (13.21 vs 13.17 ms per step: the last block's tail costs what the launch did),
                         # so it stays opt-in
-                        sums = pr.stats_vec(N * C * 2 + 64)
+                        sums = pr.stats_vec(N * C * 2 + 32)
                         self.emit('phs_norm_bwd_reduce_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
-                                  beta, int(relu), sums.data_ptr(), sums.data_ptr() + 4 * N * C * 2, coef.data_ptr(),
+                                  beta, int(relu), sums.data_ptr(), sums.data_ptr() + 8 * N * C * 2, coef.data_ptr(),
                                   dgamma, dbeta, 1)
                     else:
                         self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,

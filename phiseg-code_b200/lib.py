@@ -62,6 +62,7 @@ SIGNATURES = {
     'phs_fill_f32': [_P, c_int64, c_float, _S],
     'phs_axpy_f32': [_P, _P, c_int64, c_float, _S],
     'phs_sumsq_f32': [_P, c_int64, c_float, _P, _S],
+    'phs_weight_decay': [_P, _P, _P, c_int, c_float, _P, _S],
     'phs_argmax_f32': [_P, c_int64, c_int, _P, _S],
 }
 

@@ -78,7 +78,6 @@ class phiseg():
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
         self._hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.loss_dict = {}
         self.loss_tot = None
         self.log_dir = None
@@ -109,8 +108,25 @@ class phiseg():
             sp.h_losses = torch.zeros(sp.losses.numel(), dtype=torch.float32).pin_memory()
             if kind == 'train':
                 self._append_optimizer(sp)
+            elif kind == 'eval' and self.cfg.weight_decay is not None:
+                # the reference's validation total_loss carries the weight-decay term too (phiseg_model.py:124-128,537-549)
+                self._emit_weight_decay(sp.prog, sp, with_grad=False)
             self._progs[key] = sp
         return sp
+
+    def _weight_segments(self):
+        """(offset, count) of every filter ('weight_variables' collection, tfwrapper/utils.py:254-255) in the flat buffer."""
+        if getattr(self, '_wd_segs', None) is None:
+            rows = [[off, int(np.prod(shape))] for name, (off, shape, kind) in self.params.table.items() if kind == 'W']
+            self._wd_segs = torch.tensor(rows, dtype=torch.int64, device=self.device).reshape(-1, 2)
+        return self._wd_segs
+
+    def _emit_weight_decay(self, pr, sp, with_grad):
+        """add_weight_decay (phiseg_model.py:290-300) as ONE launch over all filters: loss term, and its gradient wd*W."""
+        P, cfg = self.params, self.cfg
+        segs = self._weight_segments()
+        pr.emit('phs_weight_decay', P.p.data_ptr(), P.g.data_ptr() if with_grad else None, segs.data_ptr(), segs.shape[0],
+                float(cfg.weight_decay), sp.losses.data_ptr() + 4 * (2 * cfg.L))
 
     def _append_optimizer(self, sp):
         """Gradient zeroing goes in front of the backward launches; weight decay, the optimizer update and the bf16
@@ -124,11 +140,7 @@ class phiseg():
         zero = pr.steps
         pr.steps = []
         if cfg.weight_decay is not None:
-            for name, (off, shape, kind) in P.table.items():
-                if kind == 'W':
-                    n = int(np.prod(shape))
-                    pr.emit('phs_sumsq_f32', P.ptr(name), n, 0.5 * cfg.weight_decay, sp.losses.data_ptr() + 4 * (2 * cfg.L))
-                    pr.emit('phs_axpy_f32', P.ptr(name, 'g'), P.ptr(name), n, float(cfg.weight_decay))
+            self._emit_weight_decay(pr, sp, with_grad=True)
         wd = pr.steps
         pr.steps = []
         gs = 1.0 / self.world
@@ -220,8 +232,11 @@ class phiseg():
             lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
         else:
             lr_t = lr
-        self._hyper_host[0] = lr_t
-        self._hyper.copy_(self._hyper_host, non_blocking=True)
+        # the step size travels as a kernel ARGUMENT (captured by value at launch) into the device word the captured
+        # optimizer node reads: a pinned staging word could be overwritten by the next step's host code before its
+        # async copy ran when steps are enqueued back to back without a synchronisation
+        L.check(self.lib.phs_fill_f32(self._hyper.data_ptr(), 1, float(lr_t), torch.cuda.current_stream().cuda_stream),
+                'phs_fill_f32')
         if self.world > 1:
             self._launch(sp, sp.grad_steps, 'grad')
             parallel.allreduce_sum_(P.g)                # one all-reduce over the flat gradient buffer (NCCL/NVLink)
@@ -285,6 +300,7 @@ class phiseg():
         """Reduced form of phiseg_model.py:530-701: checkpoint + validation ELBO with training=False + best-loss
         tracking (GED/NCC/Dice metrics are a 'next' row)."""
         self.save_weights(self.log_dir, 'model.ckpt-%d' % step)
+        _prune_checkpoints(self.log_dir, 'model.ckpt', keep=1)             # tf.train.Saver(max_to_keep=1), :144
         if hasattr(data, 'validation'):
             x_b, s_b = data.validation.next_batch(self.exp_config.batch_size)
             val = self.evaluate_losses(x_b, s_b)
@@ -292,6 +308,7 @@ class phiseg():
             if val['total_loss'] < self.best_loss:
                 self.best_loss = val['total_loss']
                 self.save_weights(self.log_dir, 'model_best_loss.ckpt-%d' % step)
+                _prune_checkpoints(self.log_dir, 'model_best_loss.ckpt', keep=2)   # saver_best_loss: max_to_keep=2, :145
 
     def evaluate_losses(self, x_b, s_b, eps=None):
         """loss_dict with training=False (phiseg_model.py:537-549)."""
@@ -504,7 +521,10 @@ class phiseg():
         if self.params.slots is not None:
             for i, sl in enumerate(self.params.slots):
                 extra['__slot%d__' % i] = sl.detach().cpu().numpy()
-        np.savez(path, **self.get_weights(), **extra)
+        # written under a temporary name and renamed into place: a crash mid-write never leaves a truncated 'latest'
+        tmp = path + '.tmp%d.npz' % os.getpid()
+        np.savez(tmp, **self.get_weights(), **extra)
+        os.replace(tmp, path)
         return path
 
     def load_weights(self, log_dir=None, type='latest', **kwargs):
@@ -516,13 +536,27 @@ class phiseg():
         if type == 'iter':
             assert 'iteration' in kwargs, "argument 'iteration' must be provided for type='iter'"
             path = os.path.join(log_dir, 'model.ckpt-%d.npz' % kwargs['iteration'])
+            candidates = [path]
         elif type in prefix:
-            path = _latest_checkpoint(log_dir, prefix[type])
+            candidates = _checkpoints(log_dir, prefix[type])            # newest first
         else:
             raise ValueError('Argument type=%s is unknown. type can be latest/iter.' % type)
-        if path is None or not os.path.exists(path):
+        candidates = [p for p in candidates if p is not None and os.path.exists(p)]
+        if not candidates:
             raise FileNotFoundError('no checkpoint of type %s in %s' % (type, log_dir))
-        data = np.load(path)
+        data = path = None
+        for cand in candidates:
+            # an unreadable newest file (e.g. written by a run that died before this code wrote atomically) falls back to
+            # the next older one instead of breaking the resume
+            try:
+                data = np.load(cand)
+                data.files
+                path = cand
+                break
+            except Exception as e:       # noqa: BLE001 - zipfile / pickle / OSError, depending on where the file is cut
+                logging.warning('checkpoint %s is unreadable (%s); trying an older one' % (cand, e))
+        if data is None:
+            raise IOError('no readable checkpoint of type %s in %s' % (type, log_dir))
         self.params.load_state_dict({k: data[k] for k in data.files if not k.startswith('__')})
         if '__global_step__' in data.files:
             self.params.step = int(data['__global_step__'])
@@ -547,15 +581,31 @@ class phiseg():
             logging.info('continuing from %s (step %d)' % (path, self.init_step))
 
 
+def _checkpoints(log_dir, prefix):
+    """All checkpoints '<prefix>[-<iteration>].npz' in log_dir, highest iteration first."""
+    found = []
+    if not os.path.isdir(log_dir):
+        return found
+    for f in os.listdir(log_dir):
+        if f.startswith(prefix) and f.endswith('.npz') and '.tmp' not in f:
+            mid = f[len(prefix):-4]
+            if mid == '':
+                found.append((0, os.path.join(log_dir, f)))
+            elif mid.startswith('-') and mid[1:].isdigit():
+                found.append((int(mid[1:]), os.path.join(log_dir, f)))
+    return [p for _, p in sorted(found, reverse=True)]
+
+
 def _latest_checkpoint(log_dir, prefix):
     """tfwrapper/utils.py:189-210: highest-iteration checkpoint with the given prefix."""
-    best, best_it = None, -1
-    if not os.path.isdir(log_dir):
-        return None
-    for f in os.listdir(log_dir):
-        if f.startswith(prefix) and f.endswith('.npz'):
-            mid = f[len(prefix):-4]
-            it = int(mid[1:]) if mid.startswith('-') and mid[1:].isdigit() else 0
-            if it > best_it:
-                best, best_it = os.path.join(log_dir, f), it
-    return best
+    c = _checkpoints(log_dir, prefix)
+    return c[0] if c else None
+
+
+def _prune_checkpoints(log_dir, prefix, keep):
+    """tf.train.Saver(max_to_keep=keep) (phiseg_model.py:144-148): delete all but the `keep` newest checkpoints."""
+    for p in _checkpoints(log_dir, prefix)[keep:]:
+        try:
+            os.remove(p)
+        except OSError:
+            pass

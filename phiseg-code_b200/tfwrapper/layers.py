@@ -63,9 +63,9 @@ def global_averagepool2D(x, name=None):
     """tf.reduce_mean over H and W: [N, C]."""
     x = _check(x, 'global_averagepool2D')
     N, H, W, C = x.shape
-    stats = torch.empty(N * C * 2, device=x.device)
+    stats = torch.empty(N * C * 2, device=x.device, dtype=torch.float64)
     L.check(L.load().phs_chan_stats(_desc(x), stats.data_ptr(), _stream()), 'phs_chan_stats')
-    return stats.view(N, C, 2)[..., 0] / float(H * W)
+    return (stats.view(N, C, 2)[..., 0] / float(H * W)).float()
 
 
 def bilinear_upsample2D(x, name, factor):

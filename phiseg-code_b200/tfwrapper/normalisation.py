@@ -34,7 +34,7 @@ def _apply(kind, x, training=None, moving_average_decay=0.99, eps=None, scope=No
     xd = L.phs_tensor(x.data_ptr(), N, H, W, C, C, L.PHS_F32)
     y = torch.empty_like(x)
     yd = L.phs_tensor(y.data_ptr(), N, H, W, C, C, L.PHS_F32)
-    stats = torch.empty(N * C * 2, device=x.device)
+    stats = torch.empty(N * C * 2, device=x.device, dtype=torch.float64)
     mean, rstd = torch.empty(N * C, device=x.device), torch.empty(N * C, device=x.device)
     if kind == 'batch_norm':
         if training is None:

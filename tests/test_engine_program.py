@@ -136,6 +136,12 @@ def test_latest_checkpoint_resolution(pkg, tmp_path):
     assert pm._latest_checkpoint(str(tmp_path), 'model.ckpt').endswith('model.ckpt-12000.npz')
     assert pm._latest_checkpoint(str(tmp_path), 'model_best_loss.ckpt').endswith('model_best_loss.ckpt-99999.npz')
     assert pm._latest_checkpoint(str(tmp_path), 'model_best_ged.ckpt') is None
+    # tf.train.Saver(max_to_keep=...) (phiseg_model.py:144-148): all but the newest `keep` files of one prefix go
+    pm._prune_checkpoints(str(tmp_path), 'model.ckpt', keep=1)
+    left = sorted(f.name for f in tmp_path.iterdir())
+    assert left == ['model.ckpt-12000.npz', 'model.ckpt-13000.txt', 'model_best_loss.ckpt-99999.npz', 'notes.npz']
+    (tmp_path / 'model.ckpt-12000.npz.tmp77.npz').write_bytes(b'')        # a half-written file is never 'latest'
+    assert pm._latest_checkpoint(str(tmp_path), 'model.ckpt').endswith('model.ckpt-12000.npz')
     # learning-rate schedule lookup (phiseg_model.py:189-190, utils.find_floor_in_list)
     assert pm.find_floor_in_list([0, 1000, 5000], 999) == 0
     assert pm.find_floor_in_list([0, 1000, 5000], 1000) == 1000

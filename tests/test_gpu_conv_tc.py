@@ -154,7 +154,7 @@ def test_conv_tc_fused_statistics(call, lib, oracle, N, H, W, Cin, Cout):
     y = oracle.conv2d_same(x.double(), w.double(), b.double())
     wf, _ = shadows(w.float())
     yb = torch.zeros(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
-    stats = torch.full((N, Cout, 2), 5.0, device='cuda')
+    stats = torch.full((N, Cout, 2), 5.0, device='cuda', dtype=torch.float64)
     call('phs_conv2d_stats', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, stats)
     assert relerr(yb, y) < 2 ** -8
     s_ref = y.sum(dim=(1, 2))
@@ -163,7 +163,7 @@ def test_conv_tc_fused_statistics(call, lib, oracle, N, H, W, Cin, Cout):
     assert relerr(stats[..., 0], s_ref) < 5e-3
     assert relerr(stats[..., 1], q_ref) < 5e-3
     # accumulating variant (the engine clears one arena for all layers): adds onto what the caller left in stats
-    acc = torch.zeros(N + 1, Cout, 2, device='cuda')    # per-sample sums + the [C][2] batch totals
+    acc = torch.zeros(N + 1, Cout, 2, device='cuda', dtype=torch.float64)    # per-sample sums + the [C][2] batch totals
     call('phs_conv2d_stats_acc', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, acc)
     assert relerr(acc[:N], stats) < 1e-4
     assert relerr(acc[N], stats.sum(dim=0)) < 1e-4

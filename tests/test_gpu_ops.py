@@ -133,7 +133,7 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
     yd, gd, bd = cu(y, torch.float32), cu(gamma, torch.float32), cu(beta, torch.float32)
     mmd, mvd = cu(mm, torch.float32), cu(mv, torch.float32)
     mmd2, mvd2 = mmd.clone(), mvd.clone()
-    stats = torch.empty(N * C * 2, device='cuda')
+    stats = torch.empty(N * C * 2, device='cuda', dtype=torch.float64)   # statistics buffers are fp64 (reproducible atomics)
     mean = torch.empty(N * C, device='cuda')
     rstd = torch.empty(N * C, device='cuda')
     call('phs_chan_stats', call.T(yd), stats)
@@ -160,7 +160,7 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
         close(mmd2, mmd, rtol=1e-6, what='fused moving mean')
         close(mvd2, mvd, rtol=1e-6, what='fused moving variance')
     gad = cu(ga, torch.float32)
-    sums = torch.empty(N * C * 2, device='cuda')
+    sums = torch.empty(N * C * 2, device='cuda', dtype=torch.float64)
     coef = torch.empty(N * C * 2, device='cuda')
     dgam = torch.zeros(C, device='cuda')
     dbet = torch.zeros(C, device='cuda')
@@ -177,11 +177,11 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
           what='dbias')
     if mode == 'bn_train':
         # fused variant: the last block of the reduction does the finalize (pre-zeroed sums + ticket counter)
-        buf = torch.zeros(N * C * 2 + 64, device='cuda')
+        buf = torch.zeros(N * C * 2 + 32, device='cuda', dtype=torch.float64)
         coef2 = torch.empty(N * C * 2, device='cuda')
         dgam2 = torch.zeros(C, device='cuda')
         dbet2 = torch.zeros(C, device='cuda')
-        call('phs_norm_bwd_reduce_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, buf, buf.data_ptr() + 4 * N * C * 2,
+        call('phs_norm_bwd_reduce_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, buf, buf.data_ptr() + 8 * N * C * 2,
              coef2, dgam2, dbet2, 1)
         close(coef2, coef.double().cpu(), rtol=1e-5, what='fused coef')
         close(dgam2, gamma.grad, rtol=2e-4, what='fused dgamma')
@@ -408,6 +408,20 @@ def test_small_helpers(call, lib):
     call('phs_axpy_f32', a, a.clone(), 100, 2.0)
     assert float(a.min()) == 7.5 and float(a.max()) == 7.5
     acc = torch.zeros(1, device='cuda')
+    # add_weight_decay over a segment table: loss += 0.5*wd*sum W^2 and g += wd*W on the listed ranges only
+    pbuf = torch.arange(40, device='cuda', dtype=torch.float32) * 0.1
+    gbuf = torch.ones(40, device='cuda')
+    segs = torch.tensor([[4, 8], [20, 12]], device='cuda', dtype=torch.int64)
+    lossw = torch.zeros(1, device='cuda')
+    call('phs_weight_decay', pbuf, gbuf, segs, 2, 0.25, lossw)
+    m = torch.zeros(40, dtype=torch.bool)
+    m[4:12] = True
+    m[20:32] = True
+    pc = pbuf.cpu()
+    close(lossw, (0.5 * 0.25 * (pc[m] ** 2).sum()).reshape(1), what='weight decay loss')
+    close(gbuf, torch.where(m, 1.0 + 0.25 * pc, torch.ones(40)), what='weight decay gradient')
+    call('phs_weight_decay', pbuf, None, segs, 2, 0.25, lossw)          # validation form: loss only
+    close(lossw, (2 * 0.5 * 0.25 * (pc[m] ** 2).sum()).reshape(1), what='weight decay loss (no gradient)')
     call('phs_sumsq_f32', a, 100, 0.5, acc)
     close(acc, torch.tensor([0.5 * 100 * 7.5 ** 2]), what='sumsq')
     src = torch.randn(2, 4, 4, 8).cuda()

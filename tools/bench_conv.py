@@ -19,7 +19,7 @@ for (N, H, W, Cin, Cout) in SHAPES:
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
     dw = torch.zeros(3, 3, Cin, Cout, device='cuda')
-    stats = torch.zeros(N, Cout, 2, device='cuda')
+    stats = torch.zeros(N, Cout, 2, device='cuda', dtype=torch.float64)
     fl = 2.0 * N * H * W * 9 * Cin * Cout
     out = '%3dx%-3d %3d->%-3d ' % (H, W, Cin, Cout)
     for kind in kinds:

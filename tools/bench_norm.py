@@ -18,7 +18,7 @@ for (N, H, W, C) in SHAPES:
     a = torch.empty_like(y); dy = torch.empty_like(y)
     mean = torch.zeros(N * C, device='cuda'); rstd = torch.ones(N * C, device='cuda')
     gamma = torch.ones(C, device='cuda'); beta = torch.zeros(C, device='cuda')
-    sums = torch.zeros(N * C * 2, device='cuda'); coef = torch.zeros(N * C * 2, device='cuda')
+    sums = torch.zeros(N * C * 2, device='cuda', dtype=torch.float64); coef = torch.zeros(N * C * 2, device='cuda')
     nbytes = N * H * W * C * 2
     out = '%3dx%-3d C=%-3d ' % (H, W, C)
     for name, passes, fn in (

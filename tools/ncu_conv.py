@@ -15,7 +15,7 @@ for (N, H, W, Cin, Cout) in [(64, 128, 128, 128, 128), (64, 128, 128, 32, 32), (
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
     dw = torch.zeros(3, 3, Cin, Cout, device='cuda')
-    stats = torch.zeros(N, Cout, 2, device='cuda')
+    stats = torch.zeros(N, Cout, 2, device='cuda', dtype=torch.float64)
     for _ in range(2):
         if kind == 'fwd':
             call('phs_conv2d', call.T(x), w, None, call.T(y), 3, 0, 0, L.IMPL_TC)

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Launch single tensor-core convolutions / normalisation kernels for an `ncu --set full` capture.
+  python tools/ncu_shapes.py KIND N,H,W,Cin,Cout [N,H,W,Cin,Cout ...]     KIND in fwd | stats | dgrad | wgrad | norm
+Each shape is launched 3 times (profile the last with ncu -s / -c or a -k regex)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import torch
+from __graft_entry__ import load_package
+load_package()
+import importlib
+L = importlib.import_module('phiseg_code_b200.lib')
+from gpu_util import Caller
+call = Caller(L)
+kind = sys.argv[1]
+for spec in sys.argv[2:]:
+    N, H, W, Cin, Cout = [int(v) for v in spec.split(',')]
+    x = torch.randn(N, H, W, Cin, device='cuda').to(torch.bfloat16)
+    dy = torch.randn(N, H, W, Cout, device='cuda').to(torch.bfloat16)
+    w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
+    wd = (torch.randn(Cin, 9 * Cout, device='cuda') * 0.05).to(torch.bfloat16)
+    y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    gx = torch.empty(N, H, W, Cin, device='cuda', dtype=torch.bfloat16)
+    dw = torch.zeros(3, 3, Cin, Cout, device='cuda')
+    stats = torch.zeros(N + 1, Cout, 2, device='cuda', dtype=torch.float64)
+    mean = torch.zeros(N * Cout, device='cuda'); rstd = torch.ones(N * Cout, device='cuda')
+    gamma = torch.ones(Cout, device='cuda'); beta = torch.zeros(Cout, device='cuda')
+    coef = torch.zeros(N * Cout * 2, device='cuda'); sums = torch.zeros(N * Cout * 2, device='cuda', dtype=torch.float64)
+    for _ in range(3):
+        if kind == 'fwd':
+            call('phs_conv2d', call.T(x), w, None, call.T(y), 3, 0, 0, L.IMPL_TC)
+        elif kind == 'stats':
+            call('phs_conv2d_stats_acc', call.T(x), w, None, call.T(y), 3, stats)
+        elif kind == 'dgrad':
+            call('phs_conv2d', call.T(dy), wd, None, call.T(gx), 3, 1, 0, L.IMPL_TC)
+        elif kind == 'wgrad':
+            call('phs_conv2d_wgrad', call.T(x), call.T(dy), dw, None, 3, 1, L.IMPL_TC)
+        elif kind == 'norm':
+            a = torch.empty_like(dy)
+            call('phs_norm_act_fwd_stats', call.T(dy), stats, L.NORM_BN_TRAIN, 1e-3, 0.99, None, None, mean, rstd, gamma, beta, 1, call.T(a))
+            call('phs_norm_bwd_reduce', call.T(a), call.T(dy), mean, rstd, gamma, beta, 1, sums)
+            call('phs_norm_bwd_apply', call.T(a), call.T(dy), mean, rstd, gamma, beta, 1, coef, call.T(y))
+    torch.cuda.synchronize()
+    call.keep.clear()

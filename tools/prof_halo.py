@@ -12,7 +12,7 @@ for (N, H, W, Cin, Cout) in [(64, 128, 128, 128, 128), (64, 128, 128, 32, 32), (
     x = torch.randn(N, H, W, Cin, device='cuda').to(torch.bfloat16)
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
-    stats = torch.zeros(N, Cout, 2, device='cuda')
+    stats = torch.zeros(N, Cout, 2, device='cuda', dtype=torch.float64)
     for _ in range(2):
         call('phs_conv2d_stats', call.T(x), w, None, call.T(y), 3, stats)
     torch.cuda.synchronize()

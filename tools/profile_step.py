@@ -22,13 +22,13 @@ def main():
     ap.add_argument('--out', default=None)
     args = ap.parse_args()
     import torch
-    from __graft_entry__ import load_package, load_oracle
+    from __graft_entry__ import load_package
     load_package()
     pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
     ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
     exp = ex.load_experiment(ex.experiment_path(args.config))
     model = pm.phiseg(exp, mode=args.mode, use_cuda_graph=False)
-    o = load_oracle()
+    import importlib as _il; o = _il.import_module("phiseg_code_b200.data")
     H = model.cfg.H
     x, s = o.synthetic_batch(args.batch, H, H, model.cfg.nlabels, seed=1)
     for _ in range(2):

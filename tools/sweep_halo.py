@@ -44,7 +44,7 @@ for (N, H, W, Cin, Cout) in SHAPES:
     x = torch.randn(N, H, W, Cin, device='cuda').to(torch.bfloat16)
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
     y = torch.empty(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
-    stats = torch.zeros(N, Cout, 2, device='cuda')
+    stats = torch.zeros(N, Cout, 2, device='cuda', dtype=torch.float64)
     out = '%3dx%-3d %3d->%-3d ' % (H, W, Cin, Cout)
     for stat in (True, False):
         for (c, s, a, g) in CFGS:

@@ -14,13 +14,13 @@ def main():
     args = ap.parse_args()
     import torch
     from torch.profiler import profile, ProfilerActivity
-    from __graft_entry__ import load_package, load_oracle
+    from __graft_entry__ import load_package
     load_package()
     pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
     ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
     exp = ex.load_experiment(ex.experiment_path(args.config))
     model = pm.phiseg(exp, mode='fast', use_cuda_graph=True)
-    o = load_oracle()
+    import importlib as _il; o = _il.import_module("phiseg_code_b200.data")
     x, s = o.synthetic_batch(args.batch, model.cfg.H, model.cfg.W, model.cfg.nlabels, seed=1)
     for _ in range(5):
         model.training_step(x, s, 1e-3)
