@@ -135,8 +135,10 @@ int phs_latent_bwd(const float* dz, const float* mu_q, const float* sp_q, const 
  * dlogits[l] (may be NULL => forward only) receive d(sum_l loss_l)/d logits[l] (buffers must be zeroed by the caller). */
 int phs_xent_multiscale(const float* const* logits, float* const* dlogits, const uint8_t* labels, int N, int H, int W,
                         int nlabels, int L, float scale, float* loss_out, void* stream);
-/* s_out = sum_l NN-upsample(logits[l]) (phiseg_model.py:304-311); optional softmax / running sum / argmax outputs. */
-int phs_aggregate_logits(const float* const* logits, int N, int H, int W, int nlabels, int L, float* s_out,
+/* s_out = sum_l NN-upsample(logits[l]) (phiseg_model.py:304-311); optional softmax / running sum / argmax outputs.
+ * rep >= 1: the N rows are rep samples of N/rep images (sample-major, row s*(N/rep) + b); softmax_accum is then
+ * [N/rep, H, W, nlabels] and receives the sum over the samples of every image (predict, phiseg_model.py:344-349). */
+int phs_aggregate_logits(const float* const* logits, int N, int H, int W, int nlabels, int L, int rep, float* s_out,
                          float* softmax_out, float* softmax_accum, int64_t* argmax_out, void* stream);
 
 /* ---- optimizer (phiseg_model.py:134-141): tf.train.AdamOptimizer, TF "epsilon-hat" form -------------------- */
@@ -154,7 +156,9 @@ int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr,
 int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
-/* dst[.., c_off + c] = src[.., c] with dtype conversion (strided channel-slice copy) */
+/* dst[.., c_off + c] = src[.., c] with dtype conversion (strided channel-slice copy).  dst->N may be a multiple of
+ * src->N: dst[n] = src[n % src->N] (the per-image part of a sampling pass, e.g. the prior's encoder pyramid, is computed
+ * once per image and tiled over the samples drawn for it, phiseg_model.py:337-353). */
 int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream);
 /* out[.., tap*Cin + ci] = x[.. shifted by tap .., ci] (zero outside the image), other channels 0; out bf16 with
  * C >= 9*Cin.  Rewrites the 3x3 convolution of a 1..7-channel network input (posteriors.py:87, priors.py:80,

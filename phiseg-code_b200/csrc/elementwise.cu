@@ -886,28 +886,31 @@ int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate
 
 // ---- helpers ---------------------------------------------------------------------------------------------
 template <typename TS, typename TD>
-__global__ void copy_cast_kernel(const TS* __restrict__ s, int lds, TD* __restrict__ d, int ldd, int C, int64_t total) {
+__global__ void copy_cast_kernel(const TS* __restrict__ s, int lds, TD* __restrict__ d, int ldd, int C, int64_t total,
+                                 int64_t src_pix) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     int64_t pix = i / C;
-    stf<TD>(d + pix * ldd + c, ldf<TS>(s + pix * lds + c));
+    stf<TD>(d + pix * ldd + c, ldf<TS>(s + (pix % src_pix) * lds + c));   // src_pix < all pixels: batch tiling
   }
 }
 
 int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream) {
   PHS_REQUIRE(src && dst && src->ptr && dst->ptr, "phs_copy_cast: null argument");
-  PHS_REQUIRE(src->N == dst->N && src->H == dst->H && src->W == dst->W && src->C == dst->C, "phs_copy_cast: shape mismatch");
-  int64_t total = (int64_t)src->N * src->H * src->W * src->C;
+  PHS_REQUIRE(src->N > 0 && dst->N % src->N == 0 && src->H == dst->H && src->W == dst->W && src->C == dst->C,
+              "phs_copy_cast: shape mismatch");
+  int64_t total = (int64_t)dst->N * src->H * src->W * src->C;
+  const int64_t sp = (int64_t)src->N * src->H * src->W;
   cudaStream_t st = (cudaStream_t)stream;
   int b = stream_blocks(total);
   if (src->dtype == PHS_F32 && dst->dtype == PHS_F32)
-    copy_cast_kernel<float, float><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total);
+    copy_cast_kernel<float, float><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
   else if (src->dtype == PHS_F32)
-    copy_cast_kernel<float, bf16><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total);
+    copy_cast_kernel<float, bf16><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
   else if (dst->dtype == PHS_F32)
-    copy_cast_kernel<bf16, float><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total);
+    copy_cast_kernel<bf16, float><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
   else
-    copy_cast_kernel<bf16, bf16><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total);
+    copy_cast_kernel<bf16, bf16><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
   return phs_check_launch("copy_cast");
 }
 

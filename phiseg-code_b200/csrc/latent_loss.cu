@@ -281,10 +281,17 @@ int phs_xent_multiscale(const float* const* logits, float* const* dlogits, const
 }
 
 __global__ void __launch_bounds__(256)
-    aggregate_logits_kernel(XentPtrs P, int N, int H, int W, int nl, int L, float* __restrict__ s_out,
+    aggregate_logits_kernel(XentPtrs P, int N, int H, int W, int nl, int L, int rep, float* __restrict__ s_out,
                             float* __restrict__ sm_out, float* __restrict__ sm_accum, int64_t* __restrict__ argmax_out) {
-  int64_t npix = (int64_t)N * H * W;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+  // N = images * rep rows (sample-major); one thread walks the rep samples of an image pixel so that their softmax
+  // sum reaches sm_accum[image pixel] without atomics and in a fixed order
+  const int64_t ipix = (int64_t)(N / rep) * H * W;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < ipix; q += (int64_t)gridDim.x * blockDim.x) {
+   float accum[XENT_MAXC];
+#pragma unroll
+   for (int c = 0; c < XENT_MAXC; ++c) accum[c] = 0.f;
+   for (int r = 0; r < rep; ++r) {
+    const int64_t p = q + r * ipix;
     int x = (int)(p % W);
     int64_t t = p / W;
     int y = (int)(t % H);
@@ -314,28 +321,36 @@ __global__ void __launch_bounds__(256)
       for (int c = 0; c < XENT_MAXC; ++c)
         if (c < nl) { e[c] = expf(acc[c] - mx); se += e[c]; }
       float inv = 1.f / se;
-      for (int c = 0; c < nl; ++c) {
-        if (sm_out) sm_out[p * nl + c] = e[c] * inv;
-        if (sm_accum) sm_accum[p * nl + c] += e[c] * inv;
-      }
+#pragma unroll
+      for (int c = 0; c < XENT_MAXC; ++c)
+        if (c < nl) {
+          if (sm_out) sm_out[p * nl + c] = e[c] * inv;
+          accum[c] += e[c] * inv;
+        }
     }
     if (argmax_out) argmax_out[p] = am;
+   }
+   if (sm_accum)
+#pragma unroll
+     for (int c = 0; c < XENT_MAXC; ++c)
+       if (c < nl) sm_accum[q * nl + c] += accum[c];
   }
 }
 
-int phs_aggregate_logits(const float* const* logits, int N, int H, int W, int nlabels, int L, float* s_out,
+int phs_aggregate_logits(const float* const* logits, int N, int H, int W, int nlabels, int L, int rep, float* s_out,
                          float* softmax_out, float* softmax_accum, int64_t* argmax_out, void* stream) {
   PHS_REQUIRE(logits, "phs_aggregate_logits: null argument");
+  PHS_REQUIRE(rep >= 1 && N % rep == 0, "phs_aggregate_logits: N=%d is not a multiple of rep=%d", N, rep);
   PHS_REQUIRE(L >= 1 && L <= XENT_MAXL && nlabels >= 1 && nlabels <= XENT_MAXC, "phs_aggregate_logits: L=%d nlabels=%d unsupported", L, nlabels);
   XentPtrs P;
   for (int l = 0; l < XENT_MAXL; ++l) {
     P.logits[l] = l < L ? logits[l] : nullptr;
     P.dlogits[l] = nullptr;
   }
-  int64_t npix = (int64_t)N * H * W;
+  int64_t npix = (int64_t)(N / rep) * H * W;
   int blocks = (int)((npix + 255) / 256 < 148 * 8 ? (npix + 255) / 256 : 148 * 8);
-  aggregate_logits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, N, H, W, nlabels, L, s_out, softmax_out, softmax_accum,
-                                                                   argmax_out);
+  aggregate_logits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, N, H, W, nlabels, L, rep, s_out, softmax_out,
+                                                                   softmax_accum, argmax_out);
   return phs_check_launch("aggregate_logits");
 }
 

@@ -707,8 +707,13 @@ def _ptr_array(ptrs):
     return arr
 
 
-def build_program(cfg, params, B, kind, device):
-    """kind:
+def build_program(cfg, params, B, kind, device, rep=1):
+    """B images.  rep > 1 (kind 'sample' only): rep samples per image are evaluated in ONE pass, batched along N
+    (sample-major: row s*B + b); everything that depends on x alone (the prior's encoder pyramid - 2.74 of its 3.16 GFLOP -
+    and, for the probabilistic U-Net, the whole U-Net) runs once per image at batch B and is tiled over the samples.  The
+    launches of that per-image part are steps[:n_enc] (sp.n_enc): predict() replays only steps[n_enc:] for further noise
+    draws of the same images (the reference re-runs the whole graph per sample, phiseg_model.py:337-353).
+    kind:
       'train'      posterior + prior(generation_mode=False) + likelihood(posterior z) + ELBO, backward
                    (phiseg_model.py:37-59,75-83,113-141), training=True
       'eval'       the same forward with training=False (validation losses, phiseg_model.py:537-549)
@@ -718,16 +723,28 @@ def build_program(cfg, params, B, kind, device):
     """
     training = kind == 'train'
     want_grad = kind == 'train'
+    assert rep == 1 or kind == 'sample', 'samples are batched along N only in the sampling program'
+    Bi = B              # images
+    B = B * rep         # rows of everything downstream of a latent sample
     b = Builder(cfg, params, B, training, want_grad, device)
     pr = b.prog
     sp = StepProgram()
-    sp.kind, sp.B, sp.prog, sp.cfg = kind, B, pr, cfg
+    sp.kind, sp.B, sp.prog, sp.cfg, sp.rep, sp.Bs = kind, Bi, pr, cfg, rep, B
+    sp.n_enc = 0
+
+    def tiled(a, out=None):
+        """per-image activation -> one copy per sample (rows s*Bi + b)"""
+        if rep == 1:
+            return a
+        t = out if out is not None else b.new(B, a.H, a.W, a.C, a.dtype)
+        pr.emit('phs_copy_cast', a.desc(), t.desc(), lane=b.lane)
+        return t
     H, W, Cx, nl, Lv, R, zd = cfg.H, cfg.W, cfg.Cx, cfg.nlabels, cfg.L, cfg.R, cfg.zdim0
     nc = cfg.nc
     f32 = L.PHS_F32
     # --- inputs
-    sp.x = b.new(B, H, W, Cx, f32)
-    sp.s = torch.zeros((B, H, W), dtype=torch.uint8, device=device)
+    sp.x = b.new(Bi, H, W, Cx, f32)
+    sp.s = torch.zeros((Bi, H, W), dtype=torch.uint8, device=device)
     shapes = cfg.latent_shapes(B)
     sp.eps = [torch.zeros(s, dtype=torch.float32, device=device) for s in shapes]
     sp.losses = torch.zeros(2 * Lv + 2, dtype=torch.float32, device=device)   # [xent_l | KL_l | pad]
@@ -741,8 +758,8 @@ def build_program(cfg, params, B, kind, device):
 
     nets = []
     if need_post:
-        pin = b.new(B, H, W, Cx + nl)
-        pr.emit('phs_posterior_input', sp.x.ptr, sp.s.data_ptr(), B, H, W, Cx, nl, pin.desc())
+        pin = b.new(Bi, H, W, Cx + nl)
+        pr.emit('phs_posterior_input', sp.x.ptr, sp.s.data_ptr(), Bi, H, W, Cx, nl, pin.desc())
         nets.append(('posterior', pin))
     if need_prior:
         nets.append(('prior', sp.x))
@@ -773,10 +790,18 @@ def build_program(cfg, params, B, kind, device):
                         cbuf = Buf(pr, B, H >> r, W >> r, nc[r] + zd * cfg.n0, b.adt)
                         cat[(net, l)] = cbuf
                         out = cbuf.act(0, nc[r])
-                    h = b.conv(h, '%s/z%d_pre_3' % (net, r), 3, nc[r], out=out)
+                    if rep > 1:
+                        h = b.conv(h, '%s/z%d_pre_3' % (net, r), 3, nc[r])
+                        if out is not None:
+                            tiled(h, out)
+                    else:
+                        h = b.conv(h, '%s/z%d_pre_3' % (net, r), 3, nc[r], out=out)
                     pre_z[(net, r)] = h
+                pre_z[(net, R - 1)] = tiled(pre_z[(net, R - 1)])
             if two:
                 b.join([1])
+            if kind == 'sample':
+                sp.n_enc = len(pr.steps)
             # --- latent hierarchy, posterior and prior level by level (posteriors.py:98-130, priors.py:92-126)
             mu = {n: [None] * Lv for n, _ in nets}
             spre = {n: [None] * Lv for n, _ in nets}
@@ -836,10 +861,11 @@ def build_program(cfg, params, B, kind, device):
             sig = {n: [None] for n, _ in nets}
             mu_out = {n: [None] for n, _ in nets}
             unet = None
-            if need_lik and b.use_lanes:
-                b.fork([2])
+            split = kind == 'sample'       # per-image part first and complete, so that it can be replayed on its own
+            if need_lik and (b.use_lanes or split):
+                b.fork([2])                 # (fork / join / set_lane are no-ops in single-stream programs)
                 b.set_lane(2)
-                unet = _probunet_unet(b, cfg, sp.x)
+                unet = _probunet_unet(b, cfg, sp.x, tiled)
                 b.set_lane(0)
             two = len(nets) == 2
             if two:
@@ -852,13 +878,17 @@ def build_program(cfg, params, B, kind, device):
                         h = b.pool(h)
                     for t in (1, 2, 3):
                         h = b.conv(h, '%s/conv_%d_%d' % (net, r, t), 3, nc[r], need_dx=not (r == 0 and t == 1))
-                mu[net][0] = b.conv(h, '%s/pre_mu' % net, 1, zd, normed=False, out_dtype=f32)
-                spre[net][0] = b.conv(h, '%s/pre_sigma' % net, 1, zd, normed=False, out_dtype=f32)
+                mu[net][0] = tiled(b.conv(h, '%s/pre_mu' % net, 1, zd, normed=False, out_dtype=f32))
+                spre[net][0] = tiled(b.conv(h, '%s/pre_sigma' % net, 1, zd, normed=False, out_dtype=f32))
                 sig[net][0] = b.new(B, 1, 1, zd, f32)
                 mu_out[net][0] = b.new(B, 1, 1, zd, f32)
             if two:
                 b.join([1])
             b.set_lane(0)
+            if split:
+                if unet is not None:
+                    b.join([2])
+                sp.n_enc = len(pr.steps)
             z = b.new(B, 1, 1, zd, f32)
             hw = (H >> (R - 1)) * (W >> (R - 1))
             _emit_latent(b, sp, 0, hw, mu, spre, sig, z, gen_mode, need_post, need_prior, gap=1, mu_out=mu_out)
@@ -868,11 +898,12 @@ def build_program(cfg, params, B, kind, device):
             if need_prior:
                 sp.prior_mu, sp.prior_sigma = mu_out['prior'], sig['prior']
             if unet is not None:
-                b.join([2])
+                if not split:
+                    b.join([2])
                 sp.logits = _probunet_head(b, cfg, sp.z[0], *unet)
         else:
             sp.z = [b.new(B, 1, 1, zd, f32)]
-        if need_lik and not (nets and b.use_lanes):
+        if need_lik and not (nets and (b.use_lanes or kind == 'sample')):
             sp.logits = _probunet_likelihood(b, cfg, sp.z[0], sp.x)
 
     # --- heads of the graph
@@ -896,9 +927,9 @@ def build_program(cfg, params, B, kind, device):
         if kind in ('sample', 'from_z', 'eval'):
             sp.s_out = torch.empty((B, H, W, nl), dtype=torch.float32, device=device)
             sp.s_out_sm = torch.empty((B, H, W, nl), dtype=torch.float32, device=device)
-            sp.sm_accum = torch.zeros((B, H, W, nl), dtype=torch.float32, device=device)
+            sp.sm_accum = torch.zeros((Bi, H, W, nl), dtype=torch.float32, device=device)   # summed over the rep samples
             sp.argmax = torch.empty((B, H, W), dtype=torch.int64, device=device)
-            pr.emit('phs_aggregate_logits', lp, B, H, W, nl, nlev, sp.s_out.data_ptr(), sp.s_out_sm.data_ptr(),
+            pr.emit('phs_aggregate_logits', lp, B, H, W, nl, nlev, rep, sp.s_out.data_ptr(), sp.s_out_sm.data_ptr(),
                     sp.sm_accum.data_ptr(), sp.argmax.data_ptr())
     sp.n_fwd = len(pr.steps)
     if want_grad:
@@ -911,6 +942,9 @@ def build_program(cfg, params, B, kind, device):
         fills.append(st)
     pr.steps[0:0] = fills
     sp.n_fwd += len(fills)
+    sp.n_fills = len(fills)
+    if sp.n_enc:
+        sp.n_enc += len(fills)
     sp.conv_flop_fwd = b.n_conv_flop
     return sp
 
@@ -1011,12 +1045,12 @@ def _probunet_likelihood(b, cfg, z, x):
     return _probunet_head(b, cfg, z, rc, hC)
 
 
-def _probunet_unet(b, cfg, x):
+def _probunet_unet(b, cfg, x, tiled=None):
     """The U-Net of likelihoods.prob_unet2D up to the point where z is tiled in (likelihoods.py:104-146): it does not
     depend on z, so it can run on its own lane next to the posterior / prior encoders."""
     nc, R, zd = cfg.nc, cfg.R, cfg.zdim0
     pr = b.prog
-    B, H, W = b.B, cfg.H, cfg.W
+    B, H, W = x.N, cfg.H, cfg.W          # images (the samples of one image share the whole U-Net)
     enc = []
     cats = {}
     h = x
@@ -1044,6 +1078,11 @@ def _probunet_unet(b, cfg, x):
                 rc = Buf(pr, B, H, W, nc[ii] + zd, b.adt)
                 out = rc.act(0, nc[ii])
             h = b.conv(h, 'likelihood/decoder/conv_%d_%d' % (jj, t), 3, nc[ii], out=out)
+    if b.B != B:
+        # one copy of the U-Net features per sample drawn for the image; z is tiled in behind them (likelihoods.py:147-151)
+        big = Buf(pr, b.B, H, W, rc.ld, b.adt)
+        tiled(rc.act(0, h.C), big.act(0, h.C))
+        rc = big
     return rc, h.C
 
 

@@ -50,7 +50,7 @@ SIGNATURES = {
     'phs_latent_fwd': [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_float, _S],
     'phs_latent_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _S],
     'phs_xent_multiscale': [POINTER(c_void_p), POINTER(c_void_p), _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _S],
-    'phs_aggregate_logits': [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _S],
+    'phs_aggregate_logits': [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _S],
     'phs_adam_step': [_P, _P, _P, _P, c_int64, c_float, _P, c_float, c_float, c_float, c_float, _S],
     'phs_momentum_step': [_P, _P, _P, c_int64, c_float, _P, c_float, c_float, _S],
     'phs_weight_prep': [_P, _P, _P, c_int, _S],

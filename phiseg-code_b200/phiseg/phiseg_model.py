@@ -96,11 +96,12 @@ class phiseg():
     # ---------------------------------------------------------------------------------------------------
     # programs
     # ---------------------------------------------------------------------------------------------------
-    def _program(self, kind, B):
-        key = (kind, B)
+    def _program(self, kind, B, rep=1):
+        """The static launch program of one graph kind at B images (rep samples per image batched along N for sampling)."""
+        key = (kind, B) if rep == 1 else (kind, B, rep)
         sp = self._progs.get(key)
         if sp is None:
-            sp = E.build_program(self.cfg, self.params, B, kind, self.device)
+            sp = E.build_program(self.cfg, self.params, B, kind, self.device, rep=rep)
             sp.graph = None
             sp.runs = 0
             sp.h_x = torch.zeros((B, self.cfg.H, self.cfg.W, self.cfg.Cx), dtype=torch.float32).pin_memory()
@@ -331,21 +332,60 @@ class phiseg():
     def _np(self, t):
         return t.detach().cpu().numpy()
 
-    def predict(self, x_in, num_samples=50, return_softmax=False):
-        """phiseg_model.py:337-353: softmax of the summed level outputs averaged over num_samples prior draws, argmax."""
+    sample_rows = 64      # images x samples evaluated per sampling pass (rows of the batch the kernels see)
+
+    def _sample_plan(self, B, num_samples):
+        """[(samples per pass, passes)]: as many samples of every image as fit sample_rows go through the network in one
+        pass, batched along N; a remainder gets its own (smaller) program."""
+        rep = max(1, min(int(num_samples), self.sample_rows // max(B, 1)))
+        plan = [(rep, num_samples // rep)]
+        if num_samples % rep:
+            plan.append((num_samples % rep, 1))
+        return [p for p in plan if p[1] > 0]
+
+    def _run_samples(self, x_in, num_samples, visit=None):
+        """num_samples prior samples of every image of x_in.  The x-only part of the graph (the prior's encoder pyramid;
+        for the probabilistic U-Net the whole U-Net) runs ONCE per image, only the noise-dependent part is replayed per
+        draw - the reference re-runs everything (phiseg_model.py:344-348).  Returns the device tensor holding the sum of
+        the samples' softmax maps [B,H,W,nlabels]; visit(sp) is called after every pass (sp.s_out etc. hold rep samples)."""
         B = int(np.shape(x_in)[0])
-        sp = self._program('sample', B)
-        self._stage_x(sp, x_in)
-        sp.sm_accum.zero_()
-        for _ in range(num_samples):
-            self._sample_once(sp)
+        st = torch.cuda.current_stream().cuda_stream
+        total = None
+        for rep, passes in self._sample_plan(B, num_samples):
+            sp = self._program('sample', B, rep)
+            self._stage_x(sp, x_in)
+            L.check(self.lib.phs_fill_f32(sp.sm_accum.data_ptr(), sp.sm_accum.numel(), 0.0, st), 'phs_fill_f32')
+            steps = sp.prog.steps
+            if not hasattr(sp, 'rest_steps'):
+                sp.enc_steps = steps[:sp.n_enc]
+                sp.rest_steps = steps[:sp.n_fills] + steps[sp.n_enc:]     # arena fills + the noise-dependent launches
+            self._launch(sp, sp.enc_steps, 'enc')
+            for _ in range(passes):
+                self._draw_eps(sp)
+                self._launch(sp, sp.rest_steps, 'rest')
+                if visit is not None:
+                    visit(sp)
+            if total is None:
+                total = sp.sm_accum
+            else:
+                L.check(self.lib.phs_axpy_f32(total.data_ptr(), sp.sm_accum.data_ptr(), total.numel(), 1.0, st), 'phs_axpy_f32')
+            self.gpu_launches += 2
+        return total
+
+    def predict(self, x_in, num_samples=50, return_softmax=False):
+        """phiseg_model.py:337-353: softmax of the summed level outputs averaged over num_samples prior draws, argmax.
+        Accumulation and argmax stay on the device; one device->host copy of the mask (and of the mean softmax)."""
+        B = int(np.shape(x_in)[0])
+        acc = self._run_samples(x_in, num_samples)
+        if getattr(self, '_argmax_img', None) is None or self._argmax_img.shape[0] != B:
+            self._argmax_img = torch.empty((B, self.cfg.H, self.cfg.W), dtype=torch.int64, device=self.device)
         st = torch.cuda.current_stream().cuda_stream
         npix = B * self.cfg.H * self.cfg.W
-        L.check(self.lib.phs_argmax_f32(sp.sm_accum.data_ptr(), npix, self.cfg.nlabels, sp.argmax.data_ptr(), st), 'phs_argmax_f32')
+        L.check(self.lib.phs_argmax_f32(acc.data_ptr(), npix, self.cfg.nlabels, self._argmax_img.data_ptr(), st), 'phs_argmax_f32')
         self.gpu_launches += 1
         if return_softmax:
-            return self._np(sp.argmax), self._np(sp.sm_accum) / num_samples
-        return self._np(sp.argmax)
+            return self._np(self._argmax_img), self._np(acc) / num_samples
+        return self._np(self._argmax_img)
 
     def predict_segmentation_sample(self, x_in, return_softmax=False, eps=None):
         """phiseg_model.py:356-364"""
@@ -435,10 +475,15 @@ class phiseg():
     def generate_samples(self, x_in, num_samples, output_all_levels=False):
         """num_samples segmentation-logit samples per image: [num_samples, B, H, W, nlabels]
         (or a list over levels of such arrays)."""
-        outs = [self.generate_samples_from_prior(x_in, output_all_levels) for _ in range(num_samples)]
         if output_all_levels:
+            outs = [self.generate_samples_from_prior(x_in, True) for _ in range(num_samples)]
             return [np.stack([o[l] for o in outs]) for l in range(len(outs[0]))]
-        return np.stack(outs)
+        B = int(np.shape(x_in)[0])
+        outs = []
+        # rows are sample-major, so a pass's s_out [rep*B,H,W,nl] is rep stacked samples as it stands
+        self._run_samples(x_in, num_samples, visit=lambda sp: outs.append(
+            self._np(sp.s_out).reshape(sp.rep, B, self.cfg.H, self.cfg.W, self.cfg.nlabels)))
+        return np.concatenate(outs, axis=0)
 
     def checks(self):
         """phiseg_model.py:160-164: a no-op in the reference too (its only check is commented out)."""

@@ -66,6 +66,41 @@ def test_programs_keep_lane_discipline(E, arch, kind, norm):
     assert sp.prog.launches() > 50
 
 
+@pytest.mark.parametrize('arch,norm,rep', [('phiseg', 'batch_norm', 1), ('phiseg', 'group_norm', 4),
+                                           ('probunet', 'batch_norm', 3), ('probunet', 'group_norm', 1)])
+def test_sampling_program_splits_per_image_and_per_sample_parts(E, arch, norm, rep, monkeypatch):
+    """predict() replays steps[:n_enc] once per batch of images and fills + steps[n_enc:] once per noise draw
+    (phiseg_model.py:337-353 re-runs everything per sample): both parts must be capturable on their own (lane
+    discipline), the per-image part must hold the whole x-only encoder (and, for the probabilistic U-Net, the U-Net) and
+    nothing that reads eps, and with rep samples per image the rows downstream of the latents are rep * B."""
+    for lanes in (True, False):
+        if not lanes:
+            monkeypatch.setenv('PHS_NO_LANES', '1')
+        B = 2
+        cfg = E.NetConfig(arch=arch, image_size=(64, 64, 1), mode='fast', norm=norm,
+                          **(dict(zdim0=6, latent_levels=1) if arch == 'probunet' else {}))
+        P = E.Params(cfg, torch.device('cpu'))
+        sp = E.build_program(cfg, P, B, 'sample', torch.device('cpu'), rep=rep)
+        steps = sp.prog.steps
+        assert 0 <= sp.n_fills < sp.n_enc < len(steps)        # (batch norm at inference has no statistics arena)
+        enc, rest = steps[:sp.n_enc], steps[:sp.n_fills] + steps[sp.n_enc:]
+        _check_lanes(enc)
+        _check_lanes(rest)
+        names_enc = [s[2] for s in enc if s[0] is not None]
+        names_rest = [s[2] for s in rest if s[0] is not None]
+        assert 'phs_latent_fwd' not in names_enc and 'phs_aggregate_logits' not in names_enc
+        assert names_rest.count('phs_latent_fwd') == cfg.L and names_rest.count('phs_aggregate_logits') == 1
+        n_enc_convs = sum(1 for n in names_enc if n.startswith('phs_conv2d'))
+        assert n_enc_convs >= 3 * cfg.R + (40 if arch == 'probunet' else 0)
+        if rep > 1:
+            assert 'phs_copy_cast' in names_enc           # per-image features tiled over the samples
+        assert sp.x.N == B and sp.Bs == rep * B
+        assert [tuple(e.shape)[0] for e in sp.eps] == [rep * B] * cfg.L
+        assert sp.s_out.shape[0] == rep * B and sp.sm_accum.shape[0] == B
+        for a in sp.logits:
+            assert a.N == rep * B
+
+
 def test_training_program_structure(E):
     cfg, P, sp = _build(E, 'phiseg', 'train')
     steps = sp.prog.steps

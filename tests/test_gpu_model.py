@@ -296,6 +296,48 @@ def test_sampling_parity(pkg, oracle, exp_name):
     assert np.abs(s2 - logits).max() < 1e-4
 
 
+@pytest.mark.parametrize('exp_name,mode,tol', [('phiseg_7_5', 'parity', 1e-6), ('phiseg_7_5_gn', 'parity', 1e-5),
+                                               ('probunet', 'parity', 1e-6), ('phiseg_7_5', 'fast', 1e-6),
+                                               ('phiseg_7_5_gn', 'fast', 5e-2), ('probunet', 'fast', 1e-6)])
+def test_batched_sampling_matches_single_samples(pkg, oracle, exp_name, mode, tol):
+    """predict() evaluates rep samples of every image in one pass (rows s*B + b) and runs the x-only part of the graph
+    once per image (phiseg_model.py:337-353 re-runs the whole graph per sample).  Row s*B + b of the batched pass must
+    equal what the one-sample program gives for image b with the same noise; replaying only the noise-dependent part
+    with new noise must do the same; the running softmax sum must be the sum over an image's samples."""
+    B, rep = 2, 3
+    model, orc, x, s, _ = _setup(pkg, oracle, exp_name, B, mode=mode)
+    big = model._program('sample', B, rep)
+    one = model._program('sample', B)
+    assert 0 < big.n_enc < len(big.prog.steps)
+    enc, rest = big.prog.steps[:big.n_enc], big.prog.steps[:big.n_fills] + big.prog.steps[big.n_enc:]
+    model._stage_x(big, x)
+    big.sm_accum.zero_()
+    model._launch(big, enc, 'enc')
+    want_acc = 0
+    for draw in range(2):
+        eps_big = oracle.synthetic_eps(model.cfg.latent_shapes(B * rep), seed=11 + draw)
+        model._draw_eps(big, eps_big)
+        model._launch(big, rest, 'rest')
+        got = big.s_out.cpu().numpy().reshape(rep, B, *big.s_out.shape[1:])
+        got_sm = big.s_out_sm.cpu().numpy().reshape(got.shape)
+        for k in range(rep):
+            eps_k = [e[k * B:(k + 1) * B] for e in eps_big]
+            model.predict_segmentation_sample(x, eps=eps_k)
+            ref = one.s_out.cpu().numpy()
+            err = np.abs(got[k] - ref).max() / max(1.0, np.abs(ref).max())
+            assert err <= tol, (draw, k, err)
+        want_acc = want_acc + got_sm.sum(axis=0)
+    assert np.abs(big.sm_accum.cpu().numpy() - want_acc).max() < 1e-5
+    # the public calls built on it: 5 samples with 4 rows per pass = passes of 2 + 2 + 1 samples per image
+    model.sample_rows = 4
+    assert model._sample_plan(B, 5) == [(2, 2), (1, 1)]
+    seg, sm = model.predict(x, num_samples=5, return_softmax=True)
+    assert seg.shape == (B, SIZE, SIZE) and np.allclose(sm.sum(-1), 1.0, atol=1e-5) and np.array_equal(seg, sm.argmax(-1))
+    smp = model.generate_samples(x, 5)
+    assert smp.shape == (5, B, SIZE, SIZE, model.cfg.nlabels) and np.all(np.isfinite(smp))
+    assert np.abs(smp[0] - smp[1]).max() > 0          # different noise per sample
+
+
 def test_posterior_samples_and_eval_losses(pkg, oracle):
     B = 2
     model, orc, x, s, eps = _setup(pkg, oracle, 'phiseg_7_5', B)

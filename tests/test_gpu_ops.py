@@ -335,12 +335,20 @@ def test_xent_multiscale(call, oracle, N, H, nl, Lv):
     sm = torch.empty_like(s_out)
     smacc = torch.ones_like(s_out)
     am = torch.empty(N, H, H, dtype=torch.int64, device='cuda')
-    call('phs_aggregate_logits', lp, N, H, H, nl, Lv, s_out, sm, smacc, am)
+    call('phs_aggregate_logits', lp, N, H, H, nl, Lv, 1, s_out, sm, smacc, am)
     tot = sum(f.detach() for f in full)
     close(s_out, tot, what='s_out')
     close(sm, torch.softmax(tot, -1), what='softmax')
     close(smacc, torch.softmax(tot, -1) + 1, what='softmax accumulate')
     assert torch.equal(am.cpu(), s_out.cpu().argmax(-1)), 'argmax must be bit-exact w.r.t. the emitted logits'
+    if N % 2 == 0:
+        # rows = 2 samples of N/2 images (sample-major): the softmax sum over an image's samples lands on the image
+        smacc2 = torch.zeros(N // 2, H, H, nl, device='cuda')
+        call('phs_aggregate_logits', lp, N, H, H, nl, Lv, 2, s_out, sm, smacc2, am)
+        close(s_out, tot, what='s_out (rep 2)')
+        smr = torch.softmax(tot, -1)
+        close(smacc2, smr[:N // 2] + smr[N // 2:], what='softmax summed over the samples of an image')
+        assert torch.equal(am.cpu(), s_out.cpu().argmax(-1))
     am2 = torch.empty_like(am)
     call('phs_argmax_f32', smacc, N * H * H, nl, am2)
     assert torch.equal(am2.cpu(), smacc.cpu().argmax(-1))
