@@ -217,15 +217,47 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    # the public call, pipelined: training_step(defer=True) stages batch k+1 (pinned host slot -> device staging slot on
+    # a copy stream) while step k runs and hands back the loss vector of step k-1; every step's inputs are copied from
+    # the host and every step's losses are read back inside the timed region, flush() collects the last one
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        loss = model.training_step(x, s, lr)
+        loss = model.training_step(x, s, lr, defer=True)
+    loss = model.flush()
     e1.record()
     torch.cuda.synchronize()
+    t_host = time.perf_counter() - t_host0
     if world > 1:
         torch.distributed.barrier()
-    dt_e2e = parallel.max_over_ranks(e0.elapsed_time(e1) * 1e-3, dev)
+    dt_e2e = parallel.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, t_host), dev)
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- sampling (img*samples/s): predict()'s device work for SAMPLES prior samples of every image of the
+    # batch - the x-only part of the graph once, the noise-dependent part once per sample, softmax accumulation on device
+    samp = None
+    if rank == 0:
+        SAMPLES = 8
+        model.sample_rows = batch            # one sample of every image per pass (rows = the training batch)
+        model.predict(x, num_samples=2)      # builds the program, eager + capture
+        model.predict(x, num_samples=2)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = model.gpu_launches
+        th = time.perf_counter()
+        s0.record()
+        seg = model.predict(x, num_samples=SAMPLES)          # host in, host mask out: this is the end-to-end number
+        s1.record()
+        torch.cuda.synchronize()
+        th = time.perf_counter() - th
+        spp = model._program('sample', batch, 1)
+        dt_s = max(s0.elapsed_time(s1) * 1e-3, th)
+        flop_s = spp.conv_flop_fwd                            # per pass incl. the x-only part
+        samp = {'value': batch * SAMPLES / dt_s, 'unit': 'image*samples/s', 'samples_per_image': SAMPLES,
+                'ms_per_sample_pass': dt_s / SAMPLES * 1e3, 'gpu_launches': model.gpu_launches - l0,
+                'what': 'phiseg.predict(x_host[%d], num_samples=%d) -> host masks: prior encoder once per image, latent '
+                        'hierarchy + likelihood once per sample, accumulation / argmax on device' % (batch, SAMPLES),
+                'mask_sum': int(seg.sum())}
 
     # ---- the dominant kernel alone (largest-FLOP convolution launch of the step), CUDA events on the launching stream
     kern = None
@@ -278,6 +310,7 @@ def main():
         'e2e': {'value': world * batch * args.steps / dt_e2e, 'unit': 'images/s',
                 'h2d_bytes_per_step': int(model.h2d_bytes), 'd2h_bytes_per_step': int(model.d2h_bytes),
                 'ms_per_step': dt_e2e / args.steps * 1e3},
+        'sampling': samp,
         'roofline_step': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                           'frac': achieved / peak_tf,
                           'what': 'whole training step: %.2f algorithmic conv GFLOP/image x %d images / device step time '

@@ -159,86 +159,140 @@ struct XentPtrs {
   float* dlogits[XENT_MAXL];
 };
 
-// One thread per 2x2 block of full-resolution pixels: the gradients of the coarser levels (nearest-neighbour up-sampled
-// heads: 4^l pixels share one head pixel) are pre-summed over the block, so level 1 needs no atomics at all and levels
-// >= 2 a quarter of them; index arithmetic is multiply-high (idx4_decode).
+// One thread per 2x2 block of full-resolution pixels, one CTA per 32x32-pixel tile; thread t owns the 2x2 block at the
+// Z-order (bit-interleaved) position t of the tile, so the 4^(l-1) threads that share a pixel of level l are a
+// contiguous, aligned run of threads: the gradients of the coarser levels (nearest-neighbour up-sampled heads: 4^l
+// pixels share one head pixel) are summed in a FIXED order - registers over the 2x2 block (level 1), warp shuffles
+// (levels 2-3), shared memory across warps (levels 4-5) - and written by exactly one thread.  No atomics up to level 5
+// (the reference uses 5 levels): the gradient, and through it the whole backward pass, is reproducible run to run
+// (fp32 atomics here were the one source of the 1e-2 run-to-run gradient differences of round 1).  Levels 6-7 span
+// several tiles and keep atomics.
+__device__ __forceinline__ int compact_even_bits(int v) {   // bits 0,2,4,6 -> 0,1,2,3
+  v &= 0x55;
+  v = (v | (v >> 1)) & 0x33;
+  v = (v | (v >> 2)) & 0x0f;
+  return v;
+}
+
 template <int NC>   // class slots compiled in (2, 4 or NC): predicated-off slots still cost issue cycles
 __global__ void __launch_bounds__(256)
     xent_multiscale_kernel(XentPtrs P, const uint8_t* __restrict__ labels, int N, int H, int W, int nl, int L,
-                           float scale, float* __restrict__ loss_out, idx4_t ix, uint32_t total) {
+                           float scale, float* __restrict__ loss_out, int tilesW, int tilesH, uint32_t total) {
+  __shared__ float red[2][8][NC];        // [level 4 | level 5][warp][class]
   float lsum[XENT_MAXL];
 #pragma unroll
   for (int l = 0; l < XENT_MAXL; ++l) lsum[l] = 0.f;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int cvu, xb, yb, n;
-    idx4_decode(i, ix, cvu, xb, yb, n);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int bx = compact_even_bits(t), by = compact_even_bits(t >> 1);   // 2x2 block inside the 32x32 tile (16 x 16 blocks)
+  for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = tile % tilesW, ty = (tile / tilesW) % tilesH, n = tile / (tilesW * tilesH);
+    const int xb = tx * 16 + bx, yb = ty * 16 + by;
+    const bool inside = 2 * xb < W && 2 * yb < H;
     // coarse-level gradient sums of this block: gblk[l][c] = sum over the block's pixels of prefix_{i<=l} g_i
     float gblk[XENT_MAXL][NC];
 #pragma unroll
     for (int l = 0; l < XENT_MAXL; ++l)
 #pragma unroll
       for (int c = 0; c < NC; ++c) gblk[l][c] = 0.f;
+    if (inside) {
 #pragma unroll
-    for (int sub = 0; sub < 4; ++sub) {
-      const int x = 2 * xb + (sub & 1), y = 2 * yb + (sub >> 1);
-      const int64_t p = ((int64_t)n * H + y) * W + x;
-      const int lab = labels[p];
-      float acc[NC], gsum[NC];
+      for (int sub = 0; sub < 4; ++sub) {
+        const int x = 2 * xb + (sub & 1), y = 2 * yb + (sub >> 1);
+        const int64_t p = ((int64_t)n * H + y) * W + x;
+        const int lab = labels[p];
+        float acc[NC], gsum[NC];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) acc[c] = gsum[c] = 0.f;
-      // pass 1 (top-down): accumulate logits, per-level loss, per-level softmax gradient g_l;
-      // d loss / d logits[j] (at full res) = sum_{i<=j} g_i: walk the levels again bottom-up for the prefix sums
-      float gl[XENT_MAXL][NC];
+        for (int c = 0; c < NC; ++c) acc[c] = gsum[c] = 0.f;
+        // pass 1 (top-down): accumulate logits, per-level loss, per-level softmax gradient g_l;
+        // d loss / d logits[j] (at full res) = sum_{i<=j} g_i: walk the levels again bottom-up for the prefix sums
+        float gl[XENT_MAXL][NC];
 #pragma unroll
-      for (int l = XENT_MAXL - 1; l >= 0; --l) {
-        if (l < L) {
-          const int hl = H >> l, wl = W >> l;
-          const float* src = P.logits[l] + (((int64_t)n * hl + (y >> l)) * wl + (x >> l)) * nl;
-          float mx = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (c < nl) { acc[c] += src[c]; mx = fmaxf(mx, acc[c]); }
-          float se = 0.f;
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (c < nl) { gl[l][c] = expf(acc[c] - mx); se += gl[l][c]; }
-          const float lse = mx + logf(se);
-          const float inv = 1.f / se;
-#pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (c < nl) {
-              gl[l][c] = (gl[l][c] * inv - (c == lab ? 1.f : 0.f)) * scale;
-              if (c == lab) lsum[l] += lse - acc[c];
-            }
-        }
-      }
-      if (P.dlogits[0]) {
-#pragma unroll
-        for (int l = 0; l < XENT_MAXL; ++l) {
+        for (int l = XENT_MAXL - 1; l >= 0; --l) {
           if (l < L) {
+            const int hl = H >> l, wl = W >> l;
+            const float* src = P.logits[l] + (((int64_t)n * hl + (y >> l)) * wl + (x >> l)) * nl;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (c < nl) { acc[c] += src[c]; mx = fmaxf(mx, acc[c]); }
+            float se = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (c < nl) { gl[l][c] = expf(acc[c] - mx); se += gl[l][c]; }
+            const float lse = mx + logf(se);
+            const float inv = 1.f / se;
 #pragma unroll
             for (int c = 0; c < NC; ++c)
               if (c < nl) {
-                gsum[c] += gl[l][c];
-                if (l == 0) P.dlogits[0][p * nl + c] = gsum[c];
-                else gblk[l][c] += gsum[c];
+                gl[l][c] = (gl[l][c] * inv - (c == lab ? 1.f : 0.f)) * scale;
+                if (c == lab) lsum[l] += lse - acc[c];
               }
+          }
+        }
+        if (P.dlogits[0]) {
+#pragma unroll
+          for (int l = 0; l < XENT_MAXL; ++l) {
+            if (l < L) {
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                if (c < nl) {
+                  gsum[c] += gl[l][c];
+                  if (l == 0) P.dlogits[0][p * nl + c] = gsum[c];
+                  else gblk[l][c] += gsum[c];
+                }
+            }
           }
         }
       }
     }
-    if (P.dlogits[0]) {
+    if (P.dlogits[0]) {     // (block-uniform: every thread takes part in the shuffles and barriers below)
 #pragma unroll
       for (int l = 1; l < XENT_MAXL; ++l) {
         if (l < L) {
           const int hl = H >> l, wl = W >> l;
           float* dst = P.dlogits[l] + (((int64_t)n * hl + (yb >> (l - 1))) * wl + (xb >> (l - 1))) * nl;
+          float v[NC];
 #pragma unroll
-          for (int c = 0; c < NC; ++c)
-            if (c < nl) {
-              if (l == 1) dst[c] = gblk[l][c];          // the block IS the level-1 pixel
-              else atomicAdd(dst + c, gblk[l][c]);
+          for (int c = 0; c < NC; ++c) v[c] = gblk[l][c];
+          if (l >= 2) {
+            // 4^(l-1) consecutive threads share the level-l pixel: butterfly inside the warp (same order every run)
+            const int span = l == 2 ? 4 : (l == 3 ? 16 : 32);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+              if (o < span)
+#pragma unroll
+                for (int c = 0; c < NC; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+          }
+          if (l <= 3) {
+            const int span = l == 1 ? 1 : (l == 2 ? 4 : 16);
+            if (inside && (t & (span - 1)) == 0)
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                if (c < nl) dst[c] = v[c];
+          } else if (l <= 5) {
+            // 2 (level 4) or 8 (level 5) warps share the pixel: per-warp sums through shared memory, added in warp order
+            if (lane == 0)
+#pragma unroll
+              for (int c = 0; c < NC; ++c) red[l - 4][warp][c] = v[c];
+            __syncthreads();
+            const int nw = l == 4 ? 2 : 8;
+            if (inside && (t & (32 * nw - 1)) == 0) {
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                if (c < nl) {
+                  float a = 0.f;
+                  for (int w2 = 0; w2 < nw; ++w2) a += red[l - 4][warp + w2][c];
+                  dst[c] = a;
+                }
             }
+            __syncthreads();
+          } else {
+            // levels 6, 7: the pixel spans several tiles (not used by the reference's 5-level configurations)
+            if (inside && lane == 0)
+#pragma unroll
+              for (int c = 0; c < NC; ++c)
+                if (c < nl) atomicAdd(dst + c, v[c]);
+          }
         }
       }
     }
@@ -264,19 +318,19 @@ int phs_xent_multiscale(const float* const* logits, float* const* dlogits, const
     PHS_REQUIRE(l >= L || P.logits[l], "phs_xent_multiscale: logits[%d] null", l);
   }
   PHS_REQUIRE(H % 2 == 0 && W % 2 == 0, "phs_xent_multiscale: odd image size");
-  int64_t nblk = (int64_t)N * (H / 2) * (W / 2);
-  PHS_REQUIRE(nblk < (1ll << 31), "phs_xent_multiscale: tensor too large");
-  int blocks = (int)((nblk + 255) / 256 < 148 * 8 ? (nblk + 255) / 256 : 148 * 8);
-  const idx4_t ix = idx4_make(1, W / 2, H / 2);
+  const int tilesW = (W + 31) / 32, tilesH = (H + 31) / 32;
+  const int64_t ntile = (int64_t)N * tilesW * tilesH;
+  PHS_REQUIRE(ntile < (1ll << 31), "phs_xent_multiscale: tensor too large");
+  const int blocks = (int)(ntile < 148 * 8 ? ntile : 148 * 8);
   if (nlabels <= 2)
-    xent_multiscale_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out, ix,
-                                                                        (uint32_t)nblk);
+    xent_multiscale_kernel<2><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out,
+                                                                        tilesW, tilesH, (uint32_t)ntile);
   else if (nlabels <= 4)
-    xent_multiscale_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out, ix,
-                                                                        (uint32_t)nblk);
+    xent_multiscale_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale, loss_out,
+                                                                        tilesW, tilesH, (uint32_t)ntile);
   else
     xent_multiscale_kernel<XENT_MAXC><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, labels, N, H, W, nlabels, L, scale,
-                                                                                loss_out, ix, (uint32_t)nblk);
+                                                                                loss_out, tilesW, tilesH, (uint32_t)ntile);
   return phs_check_launch("xent_multiscale");
 }
 

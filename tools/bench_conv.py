@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Single-layer timing of the tensor-core convolutions through the C-ABI (CUDA events, median of 20 launches)."""
+"""Single-layer timing of the tensor-core convolutions through the C-ABI (CUDA events, median of 5 bursts of 50
+back-to-back launches; the working set of every shape but the smallest exceeds L2 only partly: these are tuning numbers,
+not bench values)."""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -30,13 +32,18 @@ for (N, H, W, Cin, Cout) in SHAPES:
                 call('phs_conv2d_stats', call.T(x), w, None, call.T(y), 3, stats)
             else:
                 call('phs_conv2d_wgrad', call.T(x), call.T(dy), dw, None, 3, 1, L.IMPL_TC)
-        for _ in range(3):
+        # back-to-back bursts: single short launches on an idle GPU are timed at ramping clocks and with the launch
+        # latency inside the event pair; a burst of 50 shows the steady-state time the kernel has inside a step
+        for _ in range(20):
             run()
         ts = []
-        for _ in range(20):
+        for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); run(); e1.record(); torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e3)
+            e0.record()
+            for _ in range(50):
+                run()
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3 / 50)
         call.keep.clear()
         t = sorted(ts)[len(ts) // 2]
         out += ' %s %7.1f us %6.1f TF' % (kind, t, fl / t / 1e6)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""Launch single tensor-core convolutions / normalisation kernels for an `ncu --set full` capture.
-  python tools/ncu_shapes.py KIND N,H,W,Cin,Cout [N,H,W,Cin,Cout ...]     KIND in fwd | stats | dgrad | wgrad | norm
-Each shape is launched 3 times (profile the last with ncu -s / -c or a -k regex)."""
+"""Launch single tensor-core convolutions / normalisation kernels for an `ncu --set full` capture: every spec is warmed
+up twice and then launched ONCE between cudaProfilerStart/Stop.
+  ncu --profile-from-start off --set full --clock-control none --import-source on -o out \
+      python tools/ncu_shapes.py KIND:N,H,W,Cin,Cout [...]      KIND in fwd | stats | dgrad | wgrad | norm"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -12,9 +13,10 @@ import importlib
 L = importlib.import_module('phiseg_code_b200.lib')
 from gpu_util import Caller
 call = Caller(L)
-kind = sys.argv[1]
-for spec in sys.argv[2:]:
-    N, H, W, Cin, Cout = [int(v) for v in spec.split(',')]
+rt = torch.cuda.cudart()
+for spec in sys.argv[1:]:
+    kind, dims = spec.split(':')
+    N, H, W, Cin, Cout = [int(v) for v in dims.split(',')]
     x = torch.randn(N, H, W, Cin, device='cuda').to(torch.bfloat16)
     dy = torch.randn(N, H, W, Cout, device='cuda').to(torch.bfloat16)
     w = (torch.randn(Cout, 9 * Cin, device='cuda') * 0.05).to(torch.bfloat16)
@@ -26,7 +28,9 @@ for spec in sys.argv[2:]:
     mean = torch.zeros(N * Cout, device='cuda'); rstd = torch.ones(N * Cout, device='cuda')
     gamma = torch.ones(Cout, device='cuda'); beta = torch.zeros(Cout, device='cuda')
     coef = torch.zeros(N * Cout * 2, device='cuda'); sums = torch.zeros(N * Cout * 2, device='cuda', dtype=torch.float64)
-    for _ in range(3):
+    a = torch.empty_like(dy)
+
+    def run():
         if kind == 'fwd':
             call('phs_conv2d', call.T(x), w, None, call.T(y), 3, 0, 0, L.IMPL_TC)
         elif kind == 'stats':
@@ -36,9 +40,14 @@ for spec in sys.argv[2:]:
         elif kind == 'wgrad':
             call('phs_conv2d_wgrad', call.T(x), call.T(dy), dw, None, 3, 1, L.IMPL_TC)
         elif kind == 'norm':
-            a = torch.empty_like(dy)
             call('phs_norm_act_fwd_stats', call.T(dy), stats, L.NORM_BN_TRAIN, 1e-3, 0.99, None, None, mean, rstd, gamma, beta, 1, call.T(a))
             call('phs_norm_bwd_reduce', call.T(a), call.T(dy), mean, rstd, gamma, beta, 1, sums)
             call('phs_norm_bwd_apply', call.T(a), call.T(dy), mean, rstd, gamma, beta, 1, coef, call.T(y))
+    for _ in range(2):
+        run()
     torch.cuda.synchronize()
+    rt.cudaProfilerStart()
+    run()
+    torch.cuda.synchronize()
+    rt.cudaProfilerStop()
     call.keep.clear()
