@@ -1,6 +1,7 @@
 // C-ABI plumbing of libphiseg_sm100.so: error reporting, version/arch queries and the convolution dispatchers
 // (CUDA-core fp32 kernels vs tcgen05 tensor-core kernels).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -11,6 +12,15 @@ void phs_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int phs_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PHS_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }
 
 int phs_check_launch(const char* what) {

@@ -21,6 +21,37 @@ int phs_check_launch(const char* what);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// A step is ~1100 dependent launches; between two dependent CUDA-graph nodes the device idles for 1.2-2.5 us (launch +
+// CTA scheduling + the kernel's own prologue).  Kernels launched through phs_launch carry the programmatic-stream-
+// serialization attribute: the next kernel of the stream (graph branch) may be SCHEDULED while its predecessor still runs,
+// executes its prologue (barrier init, TMEM allocation, index arithmetic), and blocks in griddepcontrol.wait until the
+// predecessor has completed and its memory is visible.  Rule: a kernel launched through phs_launch must execute
+// PHS_PDL_PROLOGUE() before its first global-memory access (tests/test_cabi_symbols.py checks the sources for it); it
+// then also releases ITS successor (launch_dependents), so at most one kernel per stream is staged ahead.
+// PHS_PDL=0 in the environment turns the attribute off (the instructions are no-ops then).
+int phs_pdl_enabled();
+#define PHS_PDL_PROLOGUE()                                          \
+  do {                                                              \
+    asm volatile("griddepcontrol.wait;" ::: "memory");              \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
+template <typename... KArgs, typename... Args>
+static inline void phs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = phs_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Division of a 31-bit index by a launch-time constant as multiply-high + shift (a 64-bit `/` or `%` costs ~50-100
 // instructions, enough to make a 16-byte-per-thread streaming kernel ALU bound).  Valid for n < 2^31.
 struct fdiv_t { uint32_t d, m, s; };

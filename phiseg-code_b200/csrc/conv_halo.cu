@@ -153,6 +153,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  PHS_PDL_PROLOGUE();     // everything above touches only shared / tensor memory and kernel parameters
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -288,24 +289,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.stage_g) {
       // Outputs leave through shared memory and the TMA unit: a thread owns one pixel row of the sub-tile, so direct
       // stores are 16-byte pieces 2*ld bytes apart (one L2 request each, ~0.45 requests/clk/SM: measured 7 B/clk/SM).
-      // Instead every thread writes its bf16 row into a 128-row x G-channel staging tile (the TMA swizzle keeps the
-      // 16-byte st.shared conflict-free), and one thread issues a cp.async.bulk.tensor store of the tile: full
-      // 64/128-byte rows, no LSU traffic.  Two staging tiles: the store of group g-1 drains while group g is written.
+      // Instead every thread writes its bf16 row into a staging tile (the TMA swizzle keeps the 16-byte st.shared
+      // conflict-free) and the tile leaves as a cp.async.bulk.tensor store: full 64/128-byte rows, no LSU traffic.
+      // Every WARP stages and stores on its own: its 32 TMEM lanes are 4 image rows x 8 pixels of the sub-tile = one
+      // (G, 8, 4, 1) box, two staging buffers per warp, one elected lane issues the store.  No barrier couples the four
+      // epilogue warps (round 1 ran them in lockstep - named barrier + one issuing thread waiting for the previous store's
+      // read - and with every pipeline ablated the kernel still took 75-90 % of its time: that chain was the bound of all
+      // narrow layers and of every layer with fused statistics).
       const uint32_t G = p.stage_g, rowb = 2 * G;
-      const uint32_t stage_bytes = 128 * rowb;
-      const uint32_t stage0 = smem_b0 + nb * b_bytes;
-      const uint32_t xr = G == 64 ? (uint32_t)(m & 7) : (uint32_t)((m >> 1) & 3);
-      const uint32_t my_row = m * rowb;
-      const bool issuer = threadIdx.x == 64;
+      const uint32_t wbuf_bytes = 32 * rowb;
+      const uint32_t stage_all = smem_b0 + nb * b_bytes;
+      const uint32_t stage0 = stage_all + q * 2 * wbuf_bytes;
+      const uint32_t xr = G == 64 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+      const uint32_t my_row = lane * rowb;
       uint32_t sg = 0;
+      float tot[4] = {0.f, 0.f, 0.f, 0.f};      // this thread's share of the CTA's batch totals (entries m, m+128, ...)
+      // statistics leave the CTA once per image: the four warps' partials are combined through the (drained) staging
+      // buffers in a fixed order, 2*Cout fp64 atomics per CTA and image instead of 8*Cout; the batch totals accumulate
+      // in registers and leave once per CTA (they made every CTA hammer the same 2*Cout addresses at every image change)
+      auto flush_staged = [&]() {
+        if (!p.stats || st_n < 0) return;
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j * 16 < p.Cout) {
+            const int c = j * 16 + col16(lane);
+            st_shared_f32(stage0 + (uint32_t)(c * 2 + (lane & 1)) * 4u, (lane & 1) ? st_q[j] : st_s[j]);
+            st_s[j] = st_q[j] = 0.f;
+          }
+        named_bar_sync(1, 128);
+        double* dst = p.stats + (size_t)st_n * p.Cout * 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = m + 128 * k;
+          if (e < 2 * p.Cout) {
+            float a = ld_shared_f32(stage_all + (uint32_t)e * 4u);
+#pragma unroll
+            for (int w2 = 1; w2 < 4; ++w2) a += ld_shared_f32(stage_all + w2 * 2 * wbuf_bytes + (uint32_t)e * 4u);
+            atomicAdd(dst + e, (double)a);
+            tot[k] += a;
+          }
+        }
+        named_bar_sync(1, 128);
+      };
       for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
         const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
         const int n = tile / tiles_per_img;
         const int r = tile - n * tiles_per_img;
-        const int h0 = (r / p.tilesW) * TILE_H;
+        const int h0 = (r / p.tilesW) * TILE_H + 4 * q;
         const int w0 = (r % p.tilesW) * SUB_W * p.S;
         if (n != st_n) {
-          flush();
+          flush_staged();
           st_n = n;
         }
         mbar_wait(tfull(acc), aph);
@@ -318,11 +353,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (jj * 32 < p.Cout) {
               uint32_t rr[32];
               tmem_ld32(t0 + jj * 32, rr);
+              if ((((uint32_t)jj * 32) & (G - 1)) == 0) {
+                // first chunk of a group: the buffer it goes to was handed to the TMA unit two groups ago
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+              }
               tmem_ld_wait();
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[jj * 32 + i];
-              const uint32_t dst = stage0 + (sg & 1) * stage_bytes + my_row;
+              const uint32_t dst = stage0 + (sg & 1) * wbuf_bytes + my_row;
               const uint32_t slot0 = ((uint32_t)(jj * 32) & (G - 1)) >> 3;
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -336,11 +376,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               if ((((uint32_t)(jj + 1) * 32) & (G - 1)) == 0) {   // the group is complete: hand it to the TMA unit
                 fence_proxy_async();
-                if (issuer) bulk_wait_read<0>();                  // the other staging tile (group sg-1) has been read
                 __syncwarp();
-                named_bar_sync(1, 128);
-                if (issuer && !(p.dbg & 4)) {
-                  tma_store_4d(&tmY, stage0 + (sg & 1) * stage_bytes, (int)(((uint32_t)(jj * 32)) & ~(G - 1)), w0 + s * SUB_W, h0, n);
+                if (lane == 0 && !(p.dbg & 4)) {
+                  tma_store_4d(&tmY, stage0 + (sg & 1) * wbuf_bytes, (int)(((uint32_t)(jj * 32)) & ~(G - 1)), w0 + s * SUB_W, h0, n);
                   bulk_commit();
                 }
                 ++sg;
@@ -363,7 +401,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty(acc));
         stamp();
       }
-      if (issuer) bulk_wait<0>();
+      flush_staged();
+      if (p.totals) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = m + 128 * k;
+          if (e < 2 * p.Cout) atomicAdd(p.totals + e, (double)tot[k]);
+        }
+      }
+      st_n = -1;      // (the generic flush() below has nothing left to do)
+      if (lane == 0) bulk_wait<0>();
     } else {
       for (int tile = t_begin; tile < t_end; ++tile, ++tcount) {
         const uint32_t acc = tcount % p.acc_stages, aph = (tcount / p.acc_stages) & 1;
@@ -558,16 +605,16 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   rc = filter_map(w, 9 * x->C, y->C, BK, &tmB);
   if (rc) return rc;
   CUtensorMap tmY = tmA;
-  if (p.stage_g && (rc = activation_map(y, p.stage_g, SUB_W, TILE_H, 1, &tmY))) return rc;
+  if (p.stage_g && (rc = activation_map(y, p.stage_g, SUB_W, 4, 1, &tmY))) return rc;   // one epilogue warp's rows
   if (stats && !stats_prezeroed) cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)x->N * y->C, st);
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<64>, &attr))) return rc;
-    conv_halo_kernel<64><<<grid, 192, smem, st>>>(tmA, tmB, tmY, p);
+    phs_launch(conv_halo_kernel<64>, grid, 192, smem, st, tmA, tmB, tmY, p);
   } else {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_halo_kernel<32>, &attr))) return rc;
-    conv_halo_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, tmY, p);
+    phs_launch(conv_halo_kernel<32>, grid, 192, smem, st, tmA, tmB, tmY, p);
   }
   return phs_check_launch("conv_halo_kernel");
 }

@@ -227,6 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  PHS_PDL_PROLOGUE();
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -379,6 +380,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  PHS_PDL_PROLOGUE();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -554,11 +556,11 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_tc_kernel<64>, &attr))) return rc;
-    conv_tc_kernel<64><<<grid, 192, smem, st>>>(tmA, tmB, p);
+    phs_launch(conv_tc_kernel<64>, grid, 192, smem, st, tmA, tmB, p);
   } else {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_tc_kernel<32>, &attr))) return rc;
-    conv_tc_kernel<32><<<grid, 192, smem, st>>>(tmA, tmB, p);
+    phs_launch(conv_tc_kernel<32>, grid, 192, smem, st, tmA, tmB, p);
   }
   return phs_check_launch("conv_tc_kernel");
 }
@@ -619,7 +621,7 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
   static bool attr = false;
   if ((rc = allow_big_smem(wgrad_tc_kernel, &attr))) return rc;
   const int smem = stages * stage_bytes + 1024;
-  wgrad_tc_kernel<<<dim3(splits, items), 192, smem, st>>>(tmX, tmDY, p);
+  phs_launch(wgrad_tc_kernel, dim3(splits, items), 192, smem, st, tmX, tmDY, p);
   rc = phs_check_launch("wgrad_tc_kernel");
   if (rc) return rc;
   return db ? bias_grad_tc(dy, db, st) : 0;

@@ -29,6 +29,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __restrict__ y, int HW, int C, int ld,
                                                                  int pix_per_block, double* __restrict__ stats,
                                                                  double* __restrict__ totals) {
+  PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
                            double* __restrict__ sums, BwdFin fin) {
+  PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
@@ -214,7 +216,7 @@ int chan_stats_run(const phs_tensor* y, double* stats, bool with_totals, bool ze
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_chan_stats: C=%d too large", y->C);
   double* totals = with_totals ? stats + (size_t)y->N * y->C * 2 : nullptr;
-  PHS_DISPATCH_DTYPE(y->dtype, T, PHS_DISPATCH_VEC(v, V, (chan_stats_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
+  PHS_DISPATCH_DTYPE(y->dtype, T, PHS_DISPATCH_VEC(v, V, (phs_launch(chan_stats_kernel<T, V>, grid, RED_THREADS, smem, st, 
                                                             (const T*)y->ptr, HW, y->C, y->ld, ppb, stats, totals))));
   return phs_check_launch("chan_stats");
 }
@@ -237,7 +239,7 @@ int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* m
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce: C=%d too large", y->C);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_bwd_reduce_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
                                                 rstd, gamma, beta, relu, sums, BwdFin{nullptr, nullptr, nullptr, nullptr, 0}))));
   return phs_check_launch("norm_bwd_reduce");
@@ -257,7 +259,7 @@ int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float
   PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce_bn: C=%d too large", y->C);
   const BwdFin fin{counter, coef, dgamma, dbeta, accumulate};
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_bwd_reduce_kernel<T, V><<<grid, RED_THREADS, smem, st>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
                                                 rstd, gamma, beta, relu, sums, fin))));
   return phs_check_launch("norm_bwd_reduce_bn");
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(128) norm_finalize_kernel(const double* __rest
                                                             int mode, float eps, float decay, float* moving_mean,
                                                             float* moving_var, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
+  PHS_PDL_PROLOGUE();
   if (mode == PHS_NORM_GN) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N * C) return;
@@ -332,7 +335,7 @@ int phs_norm_finalize(const double* stats, int N, int HW, int C, int mode, float
   PHS_REQUIRE(mode != PHS_NORM_BN_INFER || (moving_mean && moving_var), "phs_norm_finalize: moving stats required");
   PHS_REQUIRE(mode != PHS_NORM_GN || C % max(2, C / 16) == 0, "phs_norm_finalize: C=%d not divisible into groups", C);
   int blocks = mode == PHS_NORM_GN ? (N * C + 127) / 128 : (C + 3) / 4;
-  norm_finalize_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(stats, N, HW, C, mode, eps, decay, moving_mean,
+  phs_launch(norm_finalize_kernel, blocks, 128, 0, (cudaStream_t)stream, stats, N, HW, C, mode, eps, decay, moving_mean,
                                                                  moving_var, mean, rstd);
   return phs_check_launch("norm_finalize");
 }
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(128)
                              const float* __restrict__ mean, const float* __restrict__ rstd,
                              const float* __restrict__ gamma, int N, int HW, int C, int mode, float* __restrict__ coef,
                              float* dgamma, float* dbeta, float* dbias, int accumulate) {
+  PHS_PDL_PROLOGUE();
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
@@ -404,7 +408,7 @@ int phs_norm_bwd_finalize(const double* sums, const double* stats, const float* 
   PHS_REQUIRE(sums && mean && rstd && gamma && coef, "phs_norm_bwd_finalize: null argument");
   PHS_REQUIRE(!dbias || stats, "phs_norm_bwd_finalize: dbias needs the forward stats");
   PHS_REQUIRE(mode == PHS_NORM_GN || mode == PHS_NORM_BN_TRAIN, "phs_norm_bwd_finalize: mode %d has no backward", mode);
-  norm_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, (cudaStream_t)stream>>>(sums, stats, mean, rstd, gamma, N, HW, C, mode,
+  phs_launch(norm_bwd_finalize_kernel, (C + 3) / 4, 128, 0, (cudaStream_t)stream, sums, stats, mean, rstd, gamma, N, HW, C, mode,
                                                                         coef, dgamma, dbeta, dbias, accumulate);
   return phs_check_launch("norm_bwd_finalize");
 }
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(256)
     norm_act_fwd_kernel(const T* __restrict__ y, int ldy, T* __restrict__ a, int lda, int HW, int C, int pix_per_block,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ gamma, const float* __restrict__ beta, int relu) {
+  PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < 256 ? nvec : 256;
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(256)
                               float* moving_mean, float* moving_var, float* __restrict__ mean_out,
                               float* __restrict__ rstd_out, const float* __restrict__ gamma,
                               const float* __restrict__ beta, int relu) {
+  PHS_PDL_PROLOGUE();
   const int n = blockIdx.y, N = gridDim.y;
   const int nvec = C / V;
   const int CW = nvec < 256 ? nvec : 256;
@@ -584,7 +590,7 @@ int phs_norm_act_fwd_stats(const phs_tensor* y, const double* stats, int mode, f
   dim3 grid; int ppb;
   stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);   // 77 registers: three blocks per SM
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_stats_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_act_fwd_stats_kernel<T, V>, grid, 256, 0, (cudaStream_t)stream, 
                                                 (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, ppb, stats, mode, eps,
                                                 decay, moving_mean, moving_var, mean, rstd, gamma, beta, relu))));
   return phs_check_launch("norm_act_fwd_stats");
@@ -600,7 +606,7 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
   dim3 grid; int ppb;
   stream_geometry(y->N, HW, y->C, v, 6, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_act_fwd_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_act_fwd_kernel<T, V>, grid, 256, 0, (cudaStream_t)stream, 
                                                 (const T*)y->ptr, y->ld, (T*)a->ptr, a->ld, HW, y->C, ppb, mean, rstd,
                                                 gamma, beta, relu))));
   return phs_check_launch("norm_act_fwd");
@@ -612,6 +618,7 @@ __global__ void __launch_bounds__(256, 3)
                           int lddy, int HW, int C, int pix_per_block, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma,
                           const float* __restrict__ beta, int relu, const float* __restrict__ coef) {
+  PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
   const int CW = nvec < 256 ? nvec : 256;
@@ -686,7 +693,7 @@ int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* me
   dim3 grid; int ppb;
   stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (norm_bwd_apply_kernel<T, V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_apply_kernel<T, V>, grid, 256, 0, (cudaStream_t)stream, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
                                                 HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef))));
   return phs_check_launch("norm_bwd_apply");
@@ -706,6 +713,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
     avgpool2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Ho, int Wo, idx4_t ix,
                         uint32_t total) {
+  PHS_PDL_PROLOGUE();
   const int Wi = Wo * 2;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int cv, wo, ho, n;
@@ -727,6 +735,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
     avgpool2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Ho, int Wo, idx4_t ix,
                         uint32_t total, int accumulate) {
+  PHS_PDL_PROLOGUE();
   const int Wi = Wo * 2;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int cv, wo, ho, n;
@@ -762,7 +771,7 @@ int phs_avgpool2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
   PHS_REQUIRE(total < (1ll << 31), "phs_avgpool2_fwd: tensor too large");
   const idx4_t ix = idx4_make(y->C / v, y->W, y->H);
   PHS_DISPATCH_DTYPE(x->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (avgpool2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(avgpool2_fwd_kernel<T, V>, stream_blocks(total), 256, 0, (cudaStream_t)stream, 
                                                 (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, y->H, y->W, ix, (uint32_t)total))));
   return phs_check_launch("avgpool2_fwd");
 }
@@ -776,7 +785,7 @@ int phs_avgpool2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate,
   PHS_REQUIRE(total < (1ll << 31), "phs_avgpool2_bwd: tensor too large");
   const idx4_t ix = idx4_make(dy->C / v, dy->W, dy->H);
   PHS_DISPATCH_DTYPE(dx->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (avgpool2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(avgpool2_bwd_kernel<T, V>, stream_blocks(total), 256, 0, (cudaStream_t)stream, 
                                                 (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dy->H, dy->W, ix, (uint32_t)total,
                                                 accumulate))));
   return phs_check_launch("avgpool2_bwd");
@@ -789,6 +798,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
     upsample2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int Hi, int Wi, idx4_t ix,
                          uint32_t total) {
+  PHS_PDL_PROLOGUE();
   const int Wo = 2 * Wi;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int cv, w0, h0, n;
@@ -820,6 +830,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
     upsample2_bwd_kernel(const T* __restrict__ dy, int lddy, T* __restrict__ dx, int lddx, int Hi, int Wi, idx4_t ix,
                          uint32_t total, int accumulate) {
+  PHS_PDL_PROLOGUE();
   const int Ho = 2 * Hi, Wo = 2 * Wi;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int cv, w, h, n;
@@ -864,7 +875,7 @@ int phs_upsample2_fwd(const phs_tensor* x, const phs_tensor* y, void* stream) {
   PHS_REQUIRE(total < (1ll << 31), "phs_upsample2_fwd: tensor too large");
   const idx4_t ix = idx4_make(x->C / v, x->W, x->H);
   PHS_DISPATCH_DTYPE(x->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (upsample2_fwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(upsample2_fwd_kernel<T, V>, stream_blocks(total), 256, 0, (cudaStream_t)stream, 
                                                 (const T*)x->ptr, x->ld, (T*)y->ptr, y->ld, x->H, x->W, ix, (uint32_t)total))));
   return phs_check_launch("upsample2_fwd");
 }
@@ -878,7 +889,7 @@ int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate
   PHS_REQUIRE(total < (1ll << 31), "phs_upsample2_bwd: tensor too large");
   const idx4_t ix = idx4_make(dx->C / v, dx->W, dx->H);
   PHS_DISPATCH_DTYPE(dx->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (upsample2_bwd_kernel<T, V><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(upsample2_bwd_kernel<T, V>, stream_blocks(total), 256, 0, (cudaStream_t)stream, 
                                                 (const T*)dy->ptr, dy->ld, (T*)dx->ptr, dx->ld, dx->H, dx->W, ix, (uint32_t)total,
                                                 accumulate))));
   return phs_check_launch("upsample2_bwd");
@@ -888,6 +899,7 @@ int phs_upsample2_bwd(const phs_tensor* dy, const phs_tensor* dx, int accumulate
 template <typename TS, typename TD>
 __global__ void copy_cast_kernel(const TS* __restrict__ s, int lds, TD* __restrict__ d, int ldd, int C, int64_t total,
                                  int64_t src_pix) {
+  PHS_PDL_PROLOGUE();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     int64_t pix = i / C;
@@ -904,13 +916,13 @@ int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int b = stream_blocks(total);
   if (src->dtype == PHS_F32 && dst->dtype == PHS_F32)
-    copy_cast_kernel<float, float><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
+    phs_launch(copy_cast_kernel<float, float>, b, 256, 0, st, (const float*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
   else if (src->dtype == PHS_F32)
-    copy_cast_kernel<float, bf16><<<b, 256, 0, st>>>((const float*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
+    phs_launch(copy_cast_kernel<float, bf16>, b, 256, 0, st, (const float*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
   else if (dst->dtype == PHS_F32)
-    copy_cast_kernel<bf16, float><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
+    phs_launch(copy_cast_kernel<bf16, float>, b, 256, 0, st, (const bf16*)src->ptr, src->ld, (float*)dst->ptr, dst->ld, src->C, total, sp);
   else
-    copy_cast_kernel<bf16, bf16><<<b, 256, 0, st>>>((const bf16*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
+    phs_launch(copy_cast_kernel<bf16, bf16>, b, 256, 0, st, (const bf16*)src->ptr, src->ld, (bf16*)dst->ptr, dst->ld, src->C, total, sp);
   return phs_check_launch("copy_cast");
 }
 
@@ -941,6 +953,7 @@ int phs_posterior_input(const float* x, const uint8_t* s, int N, int H, int W, i
 template <typename T>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const T* __restrict__ x, int ldx, int Cin, bf16* __restrict__ out,
                                                         int ldo, int Co, int H, int W, idx4_t ix, fdiv_t fcin, uint32_t total) {
+  PHS_PDL_PROLOGUE();
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     int v, wq, hq, n;
     idx4_decode(i, ix, v, wq, hq, n);
@@ -970,7 +983,7 @@ int phs_im2col3x3(const phs_tensor* x, const phs_tensor* out, void* stream) {
   int64_t total = (int64_t)x->N * x->H * x->W * (out->C / 8);
   PHS_REQUIRE(total < (1ll << 31), "phs_im2col3x3: tensor too large");
   const idx4_t ix = idx4_make(out->C / 8, x->W, x->H);
-  PHS_DISPATCH_DTYPE(x->dtype, T, (im2col3x3_kernel<T><<<stream_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  PHS_DISPATCH_DTYPE(x->dtype, T, (phs_launch(im2col3x3_kernel<T>, stream_blocks(total), 256, 0, (cudaStream_t)stream, 
                                       (const T*)x->ptr, x->ld, x->C, (bf16*)out->ptr, out->ld, out->C, x->H, x->W, ix,
                                       fdiv_make((uint32_t)x->C), (uint32_t)total)));
   return phs_check_launch("im2col3x3");
@@ -1020,22 +1033,24 @@ int phs_broadcast_z_bwd(const phs_tensor* g, float* dz, int accumulate, void* st
 }
 
 __global__ void fill_kernel(float* p, int64_t n, float v) {
+  PHS_PDL_PROLOGUE();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 int phs_fill_f32(float* p, int64_t n, float v, void* stream) {
   PHS_REQUIRE(p || n == 0, "phs_fill_f32: null");
   if (n == 0) return 0;
-  fill_kernel<<<stream_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  phs_launch(fill_kernel, stream_blocks(n), 256, 0, (cudaStream_t)stream, p, n, v);
   return phs_check_launch("fill");
 }
 __global__ void axpy_kernel(float* d, const float* s, int64_t n, float alpha) {
+  PHS_PDL_PROLOGUE();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] += alpha * s[i];
 }
 int phs_axpy_f32(float* dst, const float* src, int64_t n, float alpha, void* stream) {
   PHS_REQUIRE((dst && src) || n == 0, "phs_axpy_f32: null");
   if (n == 0) return 0;
-  axpy_kernel<<<stream_blocks(n), 256, 0, (cudaStream_t)stream>>>(dst, src, n, alpha);
+  phs_launch(axpy_kernel, stream_blocks(n), 256, 0, (cudaStream_t)stream, dst, src, n, alpha);
   return phs_check_launch("axpy");
 }
 

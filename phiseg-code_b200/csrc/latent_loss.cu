@@ -33,6 +33,7 @@ __global__ void latent_fwd_kernel(const float* __restrict__ mu_q, const float* _
                                   const float* __restrict__ eps, int64_t count, int use_prior_z,
                                   float* __restrict__ sigma_q, float* __restrict__ sigma_p, float* __restrict__ z,
                                   float* kl_out, float kl_scale) {
+  PHS_PDL_PROLOGUE();
   float kl = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float mq = 0.f, sq = 0.f, mp = 0.f, sp = 0.f;
@@ -93,7 +94,7 @@ int phs_latent_fwd(const float* mu_q, const float* sp_q, const float* mu_p, cons
   } else {
     int64_t count = (int64_t)N * hw * zd;
     int blocks = (int)((count + 255) / 256 < 296 ? (count + 255) / 256 : 296);
-    latent_fwd_kernel<<<blocks, 256, 0, st>>>(mu_q, sp_q, mu_p, sp_p, eps, count, use_prior_z, sigma_q, sigma_p, z, kl_out,
+    phs_launch(latent_fwd_kernel, blocks, 256, 0, st, mu_q, sp_q, mu_p, sp_p, eps, count, use_prior_z, sigma_q, sigma_p, z, kl_out,
                                               kl_scale);
   }
   return phs_check_launch("latent_fwd");
@@ -109,6 +110,7 @@ __global__ void latent_bwd_kernel(const float* __restrict__ dz, const float* __r
                                   const float* __restrict__ sigma_p, const float* __restrict__ eps, int N, int hw,
                                   int zd, int gap, float w, float* __restrict__ d_mu_q, float* __restrict__ d_sp_q,
                                   float* __restrict__ d_mu_p, float* __restrict__ d_sp_p) {
+  PHS_PDL_PROLOGUE();
   int64_t count = (int64_t)N * hw * zd;
   for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < count; j += (int64_t)gridDim.x * blockDim.x) {
     int64_t i = j;  // index into the (possibly pooled) latent
@@ -143,7 +145,7 @@ int phs_latent_bwd(const float* dz, const float* mu_q, const float* sp_q, const 
               "phs_latent_bwd: null argument");
   int64_t count = (int64_t)N * hw * zd;
   int blocks = (int)((count + 255) / 256 < 296 ? (count + 255) / 256 : 296);
-  latent_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dz, mu_q, sp_q, sigma_q, mu_p, sp_p, sigma_p, eps, N, hw, zd,
+  phs_launch(latent_bwd_kernel, blocks, 256, 0, (cudaStream_t)stream, dz, mu_q, sp_q, sigma_q, mu_p, sp_p, sigma_p, eps, N, hw, zd,
                                                              gap, kl_scale, d_mu_q, d_sp_q, d_mu_p, d_sp_p);
   return phs_check_launch("latent_bwd");
 }

@@ -30,6 +30,7 @@ template <typename TI, typename TO, int TPP, int NOUT, int MAXV>
 __global__ void __launch_bounds__(256)
     small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       TO* __restrict__ y, SmallGeom g, int accumulate) {
+  PHS_PDL_PROLOGUE();
   extern __shared__ float ws[];  // ksize 3 only: [tap][Cin][NOUT]
   const int taps = g.ks * g.ks;
   const int nvec = g.Cin / 8;
@@ -118,6 +119,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256)
     small_cin_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                      TO* __restrict__ y, SmallGeom g, int accumulate, idx4_t ix, uint32_t total) {
+  PHS_PDL_PROLOGUE();
   extern __shared__ float ws[];  // [tap][Cin][Cout]
   const int taps = g.ks * g.ks;
   for (int i = threadIdx.x; i < taps * g.Cin * g.Cout; i += blockDim.x) {
@@ -166,6 +168,7 @@ template <typename TI, typename TO, int CIN>
 __global__ void __launch_bounds__(256)
     small_cin_1x1_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                          TO* __restrict__ y, SmallGeom g, int accumulate, int64_t M) {
+  PHS_PDL_PROLOGUE();
   const int nvec = g.Cout / 8;
   const int PL = blockDim.x / nvec;
   const int cv = threadIdx.x % nvec, lp = threadIdx.x / nvec;
@@ -219,6 +222,7 @@ template <typename TS, typename TW>
 __global__ void __launch_bounds__(256)
     wgrad_small_kernel(const TS* __restrict__ s, int lds, int Cs, const TW* __restrict__ wd, int ldw, int Cw, int N,
                        int H, int W, int ks, int small_is_x, int64_t pix_per_block, int PB, float* __restrict__ dw) {
+  PHS_PDL_PROLOGUE();
   extern __shared__ float red[];  // [PB][8]
   const int taps = ks * ks;
   const int nvec = Cw / 8;
@@ -299,6 +303,7 @@ template <typename TW, typename TS, int NS>
 __global__ void __launch_bounds__(256)
     wgrad_head_kernel(const TW* __restrict__ x, int ldx, int Cw, const TS* __restrict__ dy, int lds, int Cs, int64_t M,
                       int64_t pix_per_block, float* __restrict__ dw) {
+  PHS_PDL_PROLOGUE();
   extern __shared__ float red[];  // [nvec][NS][8]
   const int nvec = Cw / 8;
   const int PL = blockDim.x / nvec;
@@ -371,7 +376,7 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
     int64_t blocks = (M * tpp + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
 #define LAUNCH_K(TI, TO, TPPV, NOUTV, MAXVV) \
-  small_cout_kernel<TI, TO, TPPV, NOUTV, MAXVV><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
+  phs_launch(small_cout_kernel<TI, TO, TPPV, NOUTV, MAXVV>, (int)blocks, 256, smem, st, (const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
 #define LAUNCH_V(TI, TO, TPPV, NOUTV)                          \
   do {                                                         \
     if (ksize != 1) LAUNCH_K(TI, TO, TPPV, NOUTV, 0);          \
@@ -412,8 +417,8 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
       if (blocks < 1) blocks = 1;
 #define LAUNCH_S1(TI, TO)                                                                                          \
   do {                                                                                                             \
-    if (x->C <= 2) small_cin_1x1_kernel<TI, TO, 2><<<(int)blocks, 256, 0, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M); \
-    else small_cin_1x1_kernel<TI, TO, 4><<<(int)blocks, 256, 0, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M);          \
+    if (x->C <= 2) phs_launch(small_cin_1x1_kernel<TI, TO, 2>, (int)blocks, 256, 0, st, (const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M); \
+    else phs_launch(small_cin_1x1_kernel<TI, TO, 4>, (int)blocks, 256, 0, st, (const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, M);          \
   } while (0)
       if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_S1(float, float);
       else if (x->dtype == PHS_F32) LAUNCH_S1(float, bf16);
@@ -431,7 +436,7 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
     if (blocks > 148 * 16) blocks = 148 * 16;
     const idx4_t ix = idx4_make(y->C / 8, x->W, x->H);
 #define LAUNCH_SI(TI, TO) \
-  small_cin_kernel<TI, TO><<<(int)blocks, 256, smem, st>>>((const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, ix, (uint32_t)total)
+  phs_launch(small_cin_kernel<TI, TO>, (int)blocks, 256, smem, st, (const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate, ix, (uint32_t)total)
     if (x->dtype == PHS_F32 && y->dtype == PHS_F32) LAUNCH_SI(float, float);
     else if (x->dtype == PHS_F32) LAUNCH_SI(float, bf16);
     else if (y->dtype == PHS_F32) LAUNCH_SI(bf16, float);
@@ -468,7 +473,7 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
     const int ns = s->C <= 2 ? 2 : s->C <= 4 ? 4 : 8;
     const size_t smem = (size_t)nvec * ns * 8 * sizeof(float);
 #define LAUNCH_WH(TW, TS, NSV)                                                                                     \
-  wgrad_head_kernel<TW, TS, NSV><<<(unsigned)splits, 256, smem, st>>>((const TW*)wd->ptr, wd->ld, wd->C, (const TS*)s->ptr, \
+  phs_launch(wgrad_head_kernel<TW, TS, NSV>, (unsigned)splits, 256, smem, st, (const TW*)wd->ptr, wd->ld, wd->C, (const TS*)s->ptr, \
                                                                       s->ld, s->C, M, ppb, dw)
 #define LAUNCH_WH_N(TW, TS)              \
   do {                                   \
@@ -498,7 +503,7 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
   dim3 grid((unsigned)splits, gy);
   const size_t smem = (size_t)PB * 8 * sizeof(float);
 #define LAUNCH_WS(TS, TW)                                                                                             \
-  wgrad_small_kernel<TS, TW><<<grid, 256, smem, st>>>((const TS*)s->ptr, s->ld, s->C, (const TW*)wd->ptr, wd->ld, wd->C, \
+  phs_launch(wgrad_small_kernel<TS, TW>, grid, 256, smem, st, (const TS*)s->ptr, s->ld, s->C, (const TW*)wd->ptr, wd->ld, wd->C, \
                                                       x->N, x->H, x->W, ksize, small_is_x, ppb, PB, dw)
   if (s->dtype == PHS_F32 && wd->dtype == PHS_F32) LAUNCH_WS(float, float);
   else if (s->dtype == PHS_F32) LAUNCH_WS(float, bf16);

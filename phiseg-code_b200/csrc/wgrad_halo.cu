@@ -93,6 +93,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  PHS_PDL_PROLOGUE();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,7 +288,7 @@ static int wgrad_halo_impl(const phs_tensor* x, const phs_tensor* dy, float* dw,
   static bool attr = false;
   if ((rc = allow_big_smem(wgrad_halo_kernel, &attr))) return rc;
   const int smem = stages * stage_bytes + 2048;
-  wgrad_halo_kernel<<<dim3(items, splits), 192, smem, st>>>(tmX, tmDY, p);
+  phs_launch(wgrad_halo_kernel, dim3(items, splits), 192, smem, st, tmX, tmDY, p);
   return phs_check_launch("wgrad_halo_kernel");
 }
 

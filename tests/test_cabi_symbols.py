@@ -58,3 +58,34 @@ def test_experiment_modules_expose_reference_attributes(pkg, name):
     assert len(names) == len(set(names))
     if pm_cfg.arch == 'phiseg':
         assert 'posterior/z0_pre_1/W' in names and 'likelihood/y_lvl0/b' in names
+
+
+def test_every_programmatically_launched_kernel_waits_for_its_predecessor():
+    """Kernels launched through phs_launch carry the programmatic-stream-serialization attribute: they may be scheduled
+    while the previous kernel of the stream still runs, so each of them MUST execute PHS_PDL_PROLOGUE() (griddepcontrol.wait)
+    before touching global memory.  Source check: every kernel name handed to phs_launch has the macro in its body, before
+    any __ldg / global pointer dereference that could matter (the macro is required to be among the first statements or
+    right after the shared-memory / tensor-memory set-up)."""
+    import re
+    csrc = os.path.join(ROOT, 'phiseg-code_b200', 'csrc')
+    src = {f: open(os.path.join(csrc, f)).read() for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))}
+    launched = set()
+    for txt in src.values():
+        for m in re.finditer(r'phs_launch\(\s*([A-Za-z_]\w*)', txt):
+            launched.add(m.group(1))
+    launched -= {'kernel', 'void'}      # the helper's own definition in common.cuh
+    assert len(launched) >= 20
+    for k in sorted(launched):
+        body = None
+        for txt in src.values():
+            m = re.search(r'__global__[^;{]*?\b' + k + r'\s*\(', txt)
+            if m:
+                i = txt.index('{', m.end())
+                depth, j = 1, i + 1
+                while depth:
+                    depth += {'{': 1, '}': -1}.get(txt[j], 0)
+                    j += 1
+                body = txt[i:j]
+                break
+        assert body is not None, 'kernel %s not found' % k
+        assert 'PHS_PDL_PROLOGUE()' in body, 'kernel %s is launched with programmatic serialization but never waits' % k
