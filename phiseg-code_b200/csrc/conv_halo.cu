@@ -28,7 +28,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int HB_MAX_A = 3, HB_MAX_B = 40;
+constexpr int HB_MAX_A = 6, HB_MAX_B = 40;
 constexpr int TILE_H = 16, SUB_W = 8;
 
 struct HaloParams {
