@@ -132,7 +132,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', default='phiseg_7_5', choices=sorted(CONFIGS))
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the config\'s)')
-    ap.add_argument('--mode', default='fast', choices=['fast', 'parity'])
+    ap.add_argument('--mode', default='fast', choices=['fast', 'parity', 'parity_tc'])
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
@@ -297,9 +297,10 @@ def main():
         'metric': metric, 'value': world * batch * args.steps / dt_dev, 'unit': 'images/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dt_dev / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if args.mode == 'fast' else 'f32', 'data': 'synthetic',
+        'dtype': {'fast': 'bf16', 'parity': 'f32', 'parity_tc': 'bf16x3 (hi/lo split operands, fp32 accumulate and activations)'}[args.mode],
+        'data': 'synthetic',
         'config': {'workload': '%s LIDC %dx%d %s, batch=%d per GPU, %d x B200 (training step: fwd + ELBO + bwd + Adam)'
-                               % (exp_name, size, size, 'bf16' if args.mode == 'fast' else 'f32', batch, world),
+                               % (exp_name, size, size, {'fast': 'bf16', 'parity': 'f32', 'parity_tc': 'bf16x3'}[args.mode], batch, world),
                    'global_batch': world * batch, 'norm': model.cfg.norm,
                    'parallelism': 'dp%d' % world if world > 1 else 'single',
                    'cuda_graph': not args.no_graph,

@@ -154,6 +154,13 @@ int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr,
  *  kpitch (row pitch of the forward layout in elements; 0 = taps*cin; larger = rows zero padded by the caller)}.
  * fwd layout  [cout][tap*cin + ci]; dgrad layout [cin][(taps-1-tap)*cout + co]. */
 int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream);
+/* Low halves of the same shadows: shadow_lo = bf16(w - bf16(w)), same table / layouts.  Together with phs_split_bf16 this
+ * gives the fp32-accurate tensor-core mode ('parity_tc'): x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (+ O(2^-17)), three bf16
+ * tcgen05 passes accumulated in fp32 through the accumulate flag of phs_conv2d / phs_conv2d_wgrad, which meets the 1e-3
+ * logit contract of the reference's fp32 path (tf.nn.conv2d, tfwrapper/layers.py:123) on the tensor cores. */
+int phs_weight_prep_lo(const float* master, void* shadow_lo, const int64_t* table, int nconv, void* stream);
+/* hi = bf16(src), lo = bf16(src - hi): src float32, hi / lo bfloat16 tensors of the same shape */
+int phs_split_bf16(const phs_tensor* src, const phs_tensor* hi, const phs_tensor* lo, void* stream);
 
 /* ---- small helpers --------------------------------------------------------------------------------------- */
 /* dst[.., c_off + c] = src[.., c] with dtype conversion (strided channel-slice copy).  dst->N may be a multiple of

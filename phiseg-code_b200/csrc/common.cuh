@@ -52,6 +52,27 @@ static inline void phs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// same, as clusters of two CTAs (cta_group::2 pairs: the two CTAs land on the two SMs of one TPC); grid.x must be even
+template <typename... KArgs, typename... Args>
+static inline void phs_launch_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = phs_pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Division of a 31-bit index by a launch-time constant as multiply-high + shift (a 64-bit `/` or `%` costs ~50-100
 // instructions, enough to make a 16-byte-per-thread streaming kernel ALU bound).  Valid for n < 2^31.
 struct fdiv_t { uint32_t d, m, s; };

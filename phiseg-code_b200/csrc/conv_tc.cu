@@ -213,7 +213,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
@@ -226,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), 512);
   PHS_PDL_PROLOGUE();
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
   tc_fence_before();
@@ -237,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // lean, warp-uniform issue loops: ring index / phase are counters, descriptors advance by adds (see conv_halo.cu)
   const int stages = p.stages, kchunks = p.kchunks, taps = p.taps, Cin = p.Cin;
-  if (warp == 0) {
+  if (warp == W_PROD) {
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -262,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++dw == 2) { dw = -1; ++dh; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     const uint32_t idesc = idesc_bf16(128, p.Cout, 0, 0);
     constexpr uint64_t LAYOUT = BK == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
     constexpr uint32_t SBO = BK == 64 ? 1024 : 512;
@@ -325,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -369,7 +369,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int t_begin = blockIdx.x * p.tiles_per_split;
   const int t_end = min(p.num_ptiles, t_begin + p.tiles_per_split);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmDY);
     for (int s = 0; s < p.stages; ++s) {
@@ -379,7 +379,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
   PHS_PDL_PROLOGUE();
   tc_fence_before();
   __syncthreads();
@@ -387,7 +387,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   const int stages = p.stages;
-  if (warp == 0) {
+  if (warp == W_PROD) {
     const int dh = p.taps == 9 ? tap / 3 - 1 : 0;
     const int dw = p.taps == 9 ? tap % 3 - 1 : 0;
     int s = 0;
@@ -408,7 +408,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       __syncwarp();
       if (++s == stages) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     const uint32_t idesc = idesc_bf16(128, p.Cout, 1, 1);
     const uint64_t layA = p.slabA == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
@@ -456,7 +456,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }

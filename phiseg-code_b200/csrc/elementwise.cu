@@ -926,6 +926,32 @@ int phs_copy_cast(const phs_tensor* src, const phs_tensor* dst, void* stream) {
   return phs_check_launch("copy_cast");
 }
 
+// fp32 -> (hi, lo) bf16 pair with x = hi + lo to 16 mantissa bits (the operand split of the fp32-accurate tensor-core
+// mode: x*w ~ hi*w_hi + lo*w_hi + hi*w_lo, three bf16 tcgen05 passes accumulated in fp32)
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ s, int lds, bf16* __restrict__ hi, int ldh,
+                                                         bf16* __restrict__ lo, int ldl, int C, int64_t total) {
+  PHS_PDL_PROLOGUE();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t pix = i / C;
+    const float v = s[pix * lds + c];
+    const bf16 h = __float2bfloat16_rn(v);
+    hi[pix * ldh + c] = h;
+    lo[pix * ldl + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+int phs_split_bf16(const phs_tensor* src, const phs_tensor* hi, const phs_tensor* lo, void* stream) {
+  PHS_REQUIRE(src && hi && lo && src->ptr && hi->ptr && lo->ptr, "phs_split_bf16: null argument");
+  PHS_REQUIRE(src->dtype == PHS_F32 && hi->dtype == PHS_BF16 && lo->dtype == PHS_BF16, "phs_split_bf16: f32 -> bf16, bf16");
+  PHS_REQUIRE(src->N == hi->N && src->H == hi->H && src->W == hi->W && src->C == hi->C && src->N == lo->N &&
+                  src->H == lo->H && src->W == lo->W && src->C == lo->C, "phs_split_bf16: shape mismatch");
+  const int64_t total = (int64_t)src->N * src->H * src->W * src->C;
+  phs_launch(split_bf16_kernel, stream_blocks(total), 256, 0, (cudaStream_t)stream, (const float*)src->ptr, src->ld,
+             (bf16*)hi->ptr, hi->ld, (bf16*)lo->ptr, lo->ld, src->C, total);
+  return phs_check_launch("split_bf16");
+}
+
 template <typename T>
 __global__ void posterior_input_kernel(const float* __restrict__ x, const uint8_t* __restrict__ s, int Cx, int nl,
                                        T* __restrict__ out, int ld, int64_t npix) {

@@ -460,8 +460,15 @@ int phs_momentum_step(float* p, const float* g, float* acc, int64_t n, float lr,
 // bf16 shadows of the conv filters.  blockIdx.y = conv, the blocks of a column walk its 32x32 (ci, co) tiles of every
 // tap: the dgrad layout keeps co contiguous (coalesced straight from the load), the forward layout is the per-tap
 // transpose and goes through shared memory so that both global accesses are coalesced.
+// part = 0: shadow = bf16(w); part = 1: shadow = bf16(w - bf16(w)), the low half of the split used by the fp32-accurate
+// tensor-core mode (w = w_hi + w_lo to 16 mantissa bits)
+__device__ __forceinline__ bf16 split_part(float v, int part) {
+  const bf16 hi = __float2bfloat16_rn(v);
+  return part ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi;
+}
+
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ master, bf16* __restrict__ shadow,
-                                                          const int64_t* __restrict__ table) {
+                                                          const int64_t* __restrict__ table, int part) {
   __shared__ float tile[32][33];
   const int64_t* e = table + (int64_t)blockIdx.y * 7;
   const float* src = master + e[0];
@@ -480,7 +487,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
       float v = 0.f;
       if (ci < cin && co < cout) {
         v = src[((int64_t)tap * cin + ci) * cout + co];   // HWIO: [tap][ci][co]
-        if (dg) dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = __float2bfloat16_rn(v);
+        if (dg) dg[(int64_t)ci * taps * cout + (int64_t)(taps - 1 - tap) * cout + co] = split_part(v, part);
       }
       tile[ty + 8 * j][tx] = v;
     }
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
     for (int j = 0; j < 4; ++j) {
       const int co = co0 + ty + 8 * j, ci = ci0 + tx;
       if (ci < cin && co < cout)
-        fwd[(int64_t)co * kpitch + (int64_t)tap * cin + ci] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+        fwd[(int64_t)co * kpitch + (int64_t)tap * cin + ci] = split_part(tile[tx][ty + 8 * j], part);
     }
     __syncthreads();
   }
@@ -498,6 +505,13 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 int phs_weight_prep(const float* master, void* shadow, const int64_t* table, int nconv, void* stream) {
   PHS_REQUIRE(master && shadow && table, "phs_weight_prep: null argument");
   if (nconv <= 0) return 0;
-  weight_prep_kernel<<<dim3(48, nconv), 256, 0, (cudaStream_t)stream>>>(master, (bf16*)shadow, table);
+  weight_prep_kernel<<<dim3(48, nconv), 256, 0, (cudaStream_t)stream>>>(master, (bf16*)shadow, table, 0);
   return phs_check_launch("weight_prep");
+}
+
+int phs_weight_prep_lo(const float* master, void* shadow_lo, const int64_t* table, int nconv, void* stream) {
+  PHS_REQUIRE(master && shadow_lo && table, "phs_weight_prep_lo: null argument");
+  if (nconv <= 0) return 0;
+  weight_prep_kernel<<<dim3(48, nconv), 256, 0, (cudaStream_t)stream>>>(master, (bf16*)shadow_lo, table, 1);
+  return phs_check_launch("weight_prep_lo");
 }

@@ -82,7 +82,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int t_begin = blockIdx.y * p.bricks_per_split;
   const int t_end = min(p.num_bricks, t_begin + p.bricks_per_split);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmDY);
     for (int s = 0; s < p.stages; ++s) {
@@ -92,7 +92,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
+  if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
   PHS_PDL_PROLOGUE();
   tc_fence_before();
   __syncthreads();
@@ -101,7 +101,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   // lean, warp-uniform issue loops (see conv_halo.cu): counters instead of divisions, descriptors advanced by adds
   const int stages = p.stages, a_boxes = p.a_boxes, nslabB = p.nslabB, n_acc = p.n_acc, nb = p.nb, nkh = p.nkh;
-  if (warp == 0) {
+  if (warp == W_PROD) {
     int s = 0;
     uint32_t ph = 0;
     const int bpi = p.bricksW * p.bricksH;
@@ -124,7 +124,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       if (++s == stages) { s = 0; ph ^= 1; }
       if (++r == bpi) { r = 0; ++n; }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     const uint32_t idesc = idesc_bf16(128, nb, 1, 1);
     const uint64_t layA = p.slabw == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
     const uint64_t layB = p.slabB == 64 ? LAYOUT_SW128 : LAYOUT_SW64;
@@ -195,7 +195,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }

@@ -35,7 +35,7 @@ class NetConfig:
                  weight_decay=None, optimizer='adam', mode='parity'):
         assert arch in ('phiseg', 'probunet'), arch
         assert norm in ('batch_norm', 'group_norm'), norm
-        assert mode in ('parity', 'fast'), mode
+        assert mode in ('parity', 'fast', 'parity_tc'), mode
         self.arch = arch
         self.H, self.W, self.Cx = image_size
         self.nlabels, self.zdim0, self.n0 = nlabels, zdim0, n0
@@ -195,7 +195,8 @@ class Params:
         self.shadow_table = {}
         self.prep_table = None
         self.pad_table = {}
-        if cfg.mode == 'fast':
+        self.shadow_lo = None
+        if cfg.mode in ('fast', 'parity_tc'):
             rows, soff = [], 0
             for name, shape, kind in self.spec:
                 if kind == 'W' and tc_eligible(shape[0], shape[2], shape[3]):
@@ -204,7 +205,7 @@ class Params:
                     self.shadow_table[name] = (soff, soff + n)
                     rows.append([self.table[name][0], soff, soff + n, taps, shape[2], shape[3], 0])
                     soff += 2 * n
-                elif kind == 'W' and pad_eligible(shape[0], shape[2], shape[3]):
+                elif kind == 'W' and cfg.mode == 'fast' and pad_eligible(shape[0], shape[2], shape[3]):
                     # network-input convs: im2col'ed 1x1 form, K = 9*cin zero padded to kp (phs_im2col3x3)
                     k9 = 9 * shape[2]
                     kp = 32 if k9 <= 32 else 64
@@ -212,6 +213,9 @@ class Params:
                     rows.append([self.table[name][0], soff, -1, 1, k9, shape[3], kp])
                     soff += kp * shape[3]
             self.shadow = torch.zeros(max(soff, 8), dtype=torch.bfloat16, device=device)
+            if cfg.mode == 'parity_tc':
+                # low halves of the filters: w = bf16(w) + bf16(w - bf16(w)) to 16 mantissa bits (phs_weight_prep_lo)
+                self.shadow_lo = torch.zeros_like(self.shadow)
             self.prep_table = torch.tensor(rows, dtype=torch.int64, device=device).reshape(-1, 7)
         self.init()
 
@@ -232,9 +236,9 @@ class Params:
     def has(self, name):
         return name in self.table or name in self.state_table
 
-    def shadow_ptr(self, name, dgrad):
+    def shadow_ptr(self, name, dgrad, lo=False):
         off = self.shadow_table[name][1 if dgrad else 0]
-        return self.shadow.data_ptr() + 2 * off
+        return (self.shadow_lo if lo else self.shadow).data_ptr() + 2 * off
 
     def pad_shadow_ptr(self, name):
         return self.shadow.data_ptr() + 2 * self.pad_table[name][0]
@@ -265,6 +269,9 @@ class Params:
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         L.check(L.load().phs_weight_prep(self.p.data_ptr(), self.shadow.data_ptr(), self.prep_table.data_ptr(),
                                          self.prep_table.shape[0], st), 'phs_weight_prep')
+        if self.shadow_lo is not None:
+            L.check(L.load().phs_weight_prep_lo(self.p.data_ptr(), self.shadow_lo.data_ptr(), self.prep_table.data_ptr(),
+                                                self.prep_table.shape[0], st), 'phs_weight_prep_lo')
 
     def state_dict(self):
         return {n: self.view(n).detach().cpu().clone() for n in self.names()}
@@ -486,6 +493,7 @@ class Builder:
         # lane so the tensor-bound wgrad kernels overlap the HBM-bound normalisation adjoints of the layers below
         self.wlane = 3 if (self.use_lanes and os.environ.get('PHS_NO_WLANE') is None) else None
         self.wlanes_used = set()
+        self._splits = {}       # parity_tc: (buffer, channel slice) -> its (hi, lo) bf16 pair, made once per activation
 
     # -- helpers ------------------------------------------------------------------------------------------
     def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
@@ -493,6 +501,18 @@ class Builder:
 
     def emit(self, name, *args):
         self.prog.emit(name, *args, lane=self.lane)
+
+    def split(self, x, cache=True):
+        """fp32 activation -> (hi, lo) bf16 pair for the three-pass tensor-core product of mode 'parity_tc'"""
+        key = (x.buf.t.data_ptr(), x.c_off, x.C)      # (the tensor outlives the Buf wrapper: the program keeps it)
+        if cache and key in self._splits:
+            return self._splits[key]
+        hi = self.new(x.N, x.H, x.W, x.C, L.PHS_BF16)
+        lo = self.new(x.N, x.H, x.W, x.C, L.PHS_BF16)
+        self.emit('phs_split_bf16', x.desc(), hi.desc(), lo.desc())
+        if cache:
+            self._splits[key] = (hi, lo)
+        return hi, lo
 
     # -- concurrency regions: fork() ... work on several lanes ... join(); the adjoints mirror them in reverse ---
     def fork(self, lanes):
@@ -531,6 +551,10 @@ class Builder:
         bias = P.ptr(scope + '/b') if P.has(scope + '/b') else None
         tc = (cfg.mode == 'fast' and tc_eligible(k, cin, cout) and x.dtype == L.PHS_BF16
               and (out_dtype in (None, L.PHS_BF16)))
+        # fp32-accurate tensor-core mode: x*w = x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, three bf16 tcgen05 passes accumulated in
+        # the fp32 output (the dropped x_lo*w_lo term is 2^-17 relative); everything else is the fp32 parity graph
+        tc3 = (cfg.mode == 'parity_tc' and tc_eligible(k, cin, cout) and x.dtype == L.PHS_F32
+               and out_dtype in (None, L.PHS_F32))
         self.n_conv_flop += 2 * x.N * x.H * x.W * k * k * cin * cout
         # network inputs (no input gradient): im2col once, then a 1x1 tensor-core conv forward and in the filter gradient
         pad_in = (cfg.mode == 'fast' and not need_dx and wname in P.pad_table and out_dtype in (None, L.PHS_BF16))
@@ -547,9 +571,25 @@ class Builder:
             w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
             w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
         ydt = self.adt if out_dtype is None else out_dtype
+
+        def conv3(src, w_hi, w_lo, b, dst, dgrad, acc):
+            """dst (+)= conv(src, w) through the (hi, lo) split: three tensor-core launches"""
+            sh, sl = src
+            self.emit('phs_conv2d', sh.desc(), w_hi, b, dst.desc(), k, dgrad, acc, L.IMPL_TC)
+            self.emit('phs_conv2d', sl.desc(), w_hi, None, dst.desc(), k, dgrad, 1, L.IMPL_TC)
+            self.emit('phs_conv2d', sh.desc(), w_lo, None, dst.desc(), k, dgrad, 1, L.IMPL_TC)
+
+        xs = None
+        if tc3:
+            xs = self.split(x)
+            w_f, w_d = P.shadow_ptr(wname, False), P.shadow_ptr(wname, True)
+            w_f_lo, w_d_lo = P.shadow_ptr(wname, False, lo=True), P.shadow_ptr(wname, True, lo=True)
         if not normed:
             y = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
-            self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
+            if tc3:
+                conv3(xs, w_f, w_f_lo, bias, y, 0, 0)
+            else:
+                self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
             a = y
             nb = None
         else:
@@ -562,6 +602,8 @@ class Builder:
                 # statistics of the following norm come out of the conv epilogue (fp32 accumulators); the arena they
                 # live in is cleared by one fill at the start of the program (build_program)
                 self.emit('phs_conv2d_stats_acc', x.desc(), w_f, bias, y.desc(), k, stats.data_ptr())
+            elif tc3:
+                conv3(xs, w_f, w_f_lo, bias, y, 0, 0)
             else:
                 self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
             if cfg.norm == 'batch_norm':
@@ -624,17 +666,33 @@ class Builder:
                     pr.emit_after(lane, wl)
                     self.lane = wl
                     self.wlanes_used.add(wl)
+                dys = None
+                if tc3:
+                    # dy splits on the chain lane (both the filter and the input gradient read them)
+                    self.lane = lane
+                    dys = self.split(dy, cache=False)
+                    if self.wlane is not None:
+                        pr.emit_after(lane, wl)
+                        self.lane = wl
                 if pad_in:
                     scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
                     self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
                     self.emit('phs_axpy_f32', P.ptr(wname, 'g'), scratch.data_ptr(), 9 * cin_real * cout, 1.0)
+                elif tc3:
+                    dW = P.ptr(wname, 'g')
+                    self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[0].desc(), dW, db, k, 1, L.IMPL_TC)
+                    self.emit('phs_conv2d_wgrad', xs[1].desc(), dys[0].desc(), dW, None, k, 1, L.IMPL_TC)
+                    self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[1].desc(), dW, db, k, 1, L.IMPL_TC)
                 else:
                     self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
                 self.lane = lane
                 if need_dx:
                     gx = x.grad()
                     acc = int(x.grad_written())
-                    self.emit('phs_conv2d', dy.desc(), w_d, None, gx.desc(), k, 1, acc, impl)
+                    if tc3:
+                        conv3(dys, w_d, w_d_lo, None, gx, 1, acc)
+                    else:
+                        self.emit('phs_conv2d', dy.desc(), w_d, None, gx.desc(), k, 1, acc, impl)
                     x.mark_grad_written()
             self.push_bwd(bwd)
         return a

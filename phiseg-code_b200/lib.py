@@ -54,6 +54,8 @@ SIGNATURES = {
     'phs_adam_step': [_P, _P, _P, _P, c_int64, c_float, _P, c_float, c_float, c_float, c_float, _S],
     'phs_momentum_step': [_P, _P, _P, c_int64, c_float, _P, c_float, c_float, _S],
     'phs_weight_prep': [_P, _P, _P, c_int, _S],
+    'phs_weight_prep_lo': [_P, _P, _P, c_int, _S],
+    'phs_split_bf16': [_T, _T, _T, _S],
     'phs_copy_cast': [_T, _T, _S],
     'phs_im2col3x3': [_T, _T, _S],
     'phs_posterior_input': [_P, _P, c_int, c_int, c_int, c_int, c_int, _T, _S],

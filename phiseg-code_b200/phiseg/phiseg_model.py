@@ -60,8 +60,10 @@ def net_config_from_experiment(exp, mode):
 class phiseg():
 
     def __init__(self, exp_config, mode=None, device=None, use_cuda_graph=True, seed=1234):
-        """mode: 'parity' (fp32 CUDA-core kernels) or 'fast' (bf16 tcgen05 tensor-core kernels, fp32 accumulate and
-        fp32 normalisation statistics / losses / optimizer).  Default: exp_config.compute_mode if present, else 'fast'."""
+        """mode: 'fast' (bf16 tcgen05 tensor-core kernels, fp32 accumulate and fp32 normalisation statistics / losses /
+        optimizer), 'parity_tc' (fp32 activations; every 32-channel-aligned convolution as three bf16 tcgen05 passes over a
+        (hi, lo) operand split = fp32-accurate products on the tensor cores: meets the 1e-3 logit contract) or 'parity'
+        (fp32 CUDA-core kernels).  Default: exp_config.compute_mode if present, else 'fast'."""
         self.exp_config = exp_config
         if not torch.cuda.is_available():
             raise RuntimeError('phiseg-code_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
@@ -85,6 +87,8 @@ class phiseg():
         self.gpu_launches = 0
         self.world = 1
         self.rank = 0
+        # 'eager': grad graph -> NCCL all-reduce -> optimizer graph; 'graph': bucketed all-reduces captured inside the step
+        self.dp_mode = os.environ.get('PHS_DP_MODE', 'eager')
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
@@ -155,6 +159,9 @@ class phiseg():
         if P.shadow is not None and P.prep_table.numel():
             pr.emit('phs_weight_prep', P.p.data_ptr(), P.shadow.data_ptr(), P.prep_table.data_ptr(),
                     P.prep_table.shape[0])
+            if P.shadow_lo is not None:
+                pr.emit('phs_weight_prep_lo', P.p.data_ptr(), P.shadow_lo.data_ptr(), P.prep_table.data_ptr(),
+                        P.prep_table.shape[0])
         opt = pr.steps
         if self.world > 1:
             # weight decay is a local, identical term on every replica: it is added AFTER the all-reduce (scaled by
@@ -167,9 +174,14 @@ class phiseg():
                 pr.emit('phs_weight_decay', P.p.data_ptr(), None, segs.data_ptr(), segs.shape[0],
                         float(cfg.weight_decay), sp.losses.data_ptr() + 4 * (2 * cfg.L))
                 wd = pr.steps
-            bwd = parallel.insert_gradient_allreduce(bwd, P, self.world)
-        sp.grad_steps = fwd + zero + bwd + wd           # produces losses and the (all-reduced) gradient
-        sp.opt_steps = opt                               # consumes it
+            if self.dp_mode == 'graph':
+                bwd = parallel.insert_gradient_allreduce(bwd, P, self.world)
+        if self.world > 1 and self.dp_mode != 'graph':
+            sp.grad_steps = fwd + zero + bwd            # produces losses and the LOCAL gradient
+            sp.opt_steps = wd + opt                     # after the all-reduce: weight decay, optimizer, shadow refresh
+        else:
+            sp.grad_steps = fwd + zero + bwd + wd       # produces losses and the (all-reduced) gradient
+            sp.opt_steps = opt                          # consumes it
         pr.steps = sp.grad_steps + sp.opt_steps
 
     def _launch(self, sp, steps, tag):
@@ -254,9 +266,16 @@ class phiseg():
         # async copy ran when steps are enqueued back to back without a synchronisation
         L.check(self.lib.phs_fill_f32(self._hyper.data_ptr(), 1, float(lr_t), torch.cuda.current_stream().cuda_stream),
                 'phs_fill_f32')
-        # data parallel: the all-reduce of the flat gradient buffer is PART of the program (NCCL launches on a
-        # communication lane, captured into the same CUDA graph), bucketed so that it overlaps the backward tail
-        self._launch(sp, sp.prog.steps, 'step')
+        if self.world > 1 and self.dp_mode != 'graph':
+            # default data-parallel path: gradient graph, ONE NCCL all-reduce over the flat gradient buffer (NVLink),
+            # optimizer graph
+            self._launch(sp, sp.grad_steps, 'grad')
+            parallel.allreduce_sum_(P.g)
+            self._launch(sp, sp.opt_steps, 'opt')
+        else:
+            # single GPU, or PHS_DP_MODE=graph: the bucketed all-reduces are part of the program (NCCL launches on a
+            # communication lane, captured into the same CUDA graph, overlapping the backward tail)
+            self._launch(sp, sp.prog.steps, 'step')
         P.step = t
 
     def _read_losses(self, sp):

@@ -36,6 +36,7 @@ def main():
     for it in range(3):                      # eager, capture + replay, replay: the collectives live inside the graph
         losses.append(dp.training_step(x[sl], s[sl], lr=0.0, eps=[e[sl] for e in eps]))
     assert dp._program('train', b).graphs, 'data-parallel step was not captured into a CUDA graph'
+    print('rank %d: 3 data-parallel steps done (dp_mode=%s)' % (rank, dp.dp_mode), flush=True)
     assert abs(losses[0] - losses[2]) <= 1e-6 * abs(losses[0]), losses
     g_dp = dp.params.g.detach().clone() / world
     loss_sum = torch.tensor([losses[2]], dtype=torch.float64, device='cuda')

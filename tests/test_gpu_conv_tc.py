@@ -98,6 +98,55 @@ def test_conv_tc_fwd_dgrad_wgrad(call, lib, oracle, N, H, W, Cin, Cout, k):
     assert e < 4e-5, 'conv wgrad accumulate: %.3e' % e
 
 
+PAIR_CASES = [  # N, H, W, Cin, Cout: shapes the halo kernel takes (H % 16 == 0, W % 8 == 0)
+    (2, 32, 32, 128, 128),       # streamed filter, two 64-channel chunks
+    (3, 16, 16, 192, 192),       # odd number of tiles: rank 1 of the last pair owns an empty tile
+    (2, 64, 64, 64, 128),
+    (1, 16, 16, 384, 192),       # six chunks
+    (2, 32, 32, 32, 192),        # BK = 32
+    (2, 128, 128, 32, 32),       # filter resident in both halves
+    (1, 16, 8, 64, 64),          # a single tile: one CTA of the pair idles
+    (5, 16, 16, 128, 256),
+]
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', PAIR_CASES)
+def test_conv_halo_cta_pairs(call, lib, oracle, monkeypatch, N, H, W, Cin, Cout):
+    """conv_halo_kernel<BK, PAIR=true> (cta_group::2: clusters of two CTAs, each staging half of every filter tile, one
+    M=256 tcgen05.mma per tap issued by the leader): forward with bf16 / fp32 outputs, fused statistics, accumulation and
+    the input gradient against the fp64 oracle on the same bf16-rounded operands - and bit-identical to the single-CTA
+    kernel for fp32 outputs (same products, same accumulation order inside the tensor core)."""
+    g = torch.Generator().manual_seed(N * 100 + Cin + Cout + H)
+    x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3, 3, Cin, Cout, generator=g) * (1.0 / np.sqrt(9 * Cin))).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g)
+    gy = torch.randn(N, H, W, Cout, generator=g).to(torch.bfloat16)
+    xr = x.double().requires_grad_(True)
+    y = oracle.conv2d_same(xr, w.double(), b.double())
+    y.backward(gy.double())
+    xd, gyd, bd = x.cuda(), gy.cuda(), b.cuda()
+    wf, wdg = shadows(w.float())
+    y1 = torch.zeros(N, H, W, Cout, device='cuda')
+    call('phs_conv2d', call.T(xd), wf, bd, call.T(y1), 3, 0, 0, lib.IMPL_TC)
+    monkeypatch.setenv('PHS_HALO_PAIR', '1')
+    y2 = torch.zeros(N, H, W, Cout, device='cuda')
+    call('phs_conv2d', call.T(xd), wf, bd, call.T(y2), 3, 0, 0, lib.IMPL_TC)
+    torch.cuda.synchronize()
+    assert relerr(y2, y) < 2e-5, 'pair fwd f32: %.3e' % relerr(y2, y)
+    assert torch.equal(y1, y2), 'pair and single-CTA kernels differ'
+    call('phs_conv2d', call.T(xd), wf, None, call.T(y2), 3, 0, 1, lib.IMPL_TC)
+    assert relerr(y2, 2 * y - b.double()) < 4e-5
+    yb = torch.zeros(N, H, W, Cout, device='cuda', dtype=torch.bfloat16)
+    acc = torch.zeros(N + 1, Cout, 2, device='cuda', dtype=torch.float64)
+    call('phs_conv2d_stats_acc', call.T(xd), wf, bd, call.T(yb), 3, acc)
+    assert relerr(yb, y) < 2 ** -8
+    assert relerr(acc[:N, :, 0], y.sum(dim=(1, 2))) < 5e-3 and relerr(acc[:N, :, 1], (y * y).sum(dim=(1, 2))) < 5e-3
+    assert relerr(acc[N], acc[:N].sum(dim=0)) < 1e-6
+    gxd = torch.zeros(N, H, W, Cin, device='cuda')
+    call('phs_conv2d', call.T(gyd), wdg, None, call.T(gxd), 3, 1, 0, lib.IMPL_TC)
+    assert relerr(gxd, xr.grad) < 2e-5, 'pair dgrad: %.3e' % relerr(gxd, xr.grad)
+
+
 def test_conv_tc_channel_slices(call, lib, oracle):
     """zero-copy tf.concat: operands addressed as channel slices of wider buffers (ld > C)"""
     g = torch.Generator().manual_seed(11)

@@ -1,0 +1,24 @@
+set -x
+mkdir -p gpurun_out/r2
+timeout 900 python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_ops.py -m gpu -q -x -k 'not pairs' 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_conv_tc.py -m gpu -q -k 'pairs' 2>&1 | tail -15
+timeout 1200 python -m pytest tests/test_gpu_model.py -m gpu -q -s -k "parity" 2>&1 | grep -E "passed|failed|FAILED|worst relative|logit diff|Error|assert" | head -40
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/r2/bench4.json 2> gpurun_out/r2/bench4.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r2/bench4.json'))
+print('ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'sampling', d['sampling']['value'], 'kernel us', d['roofline']['us_per_launch'], d['roofline']['frac'])
+"
+tail -2 gpurun_out/r2/bench4.err
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --mode parity_tc > gpurun_out/r2/bench4_ptc.json 2> gpurun_out/r2/bench4_ptc.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r2/bench4_ptc.json'))
+print('parity_tc ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'sampling', d['sampling']['value'])
+"
+tail -2 gpurun_out/r2/bench4_ptc.err
+SWEEP_SHAPES="64,128,128,128,128" SWEEP_CFGS="2/-/-/-,1/2/-/-,1/1/-/-" timeout 300 python tools/sweep_halo.py trace > gpurun_out/r2/trace2.txt 2>&1
+cut -c1-420 gpurun_out/r2/trace2.txt
+SWEEP_SHAPES="64,128,128,128,128;64,64,64,192,192;64,128,128,64,128;64,32,32,128,128;64,16,16,192,192;64,32,32,256,192;64,128,128,32,192" SWEEP_CFGS="2/-/-/-" timeout 300 python tools/sweep_halo.py > gpurun_out/r2/sweep_pair0.txt 2>&1
+PHS_HALO_PAIR=1 SWEEP_SHAPES="64,128,128,128,128;64,64,64,192,192;64,128,128,64,128;64,32,32,128,128;64,16,16,192,192;64,32,32,256,192;64,128,128,32,192" SWEEP_CFGS="2/-/-/-" timeout 300 python tools/sweep_halo.py > gpurun_out/r2/sweep_pair1.txt 2>&1
+cat gpurun_out/r2/sweep_pair0.txt gpurun_out/r2/sweep_pair1.txt

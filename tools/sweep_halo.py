@@ -17,6 +17,8 @@ SHAPES = [(64, 128, 128, 128, 128), (64, 128, 128, 32, 32), (64, 64, 64, 64, 64)
           (64, 16, 16, 192, 192), (64, 16, 16, 64, 64), (64, 32, 32, 256, 192)]
 CFGS = [('2', None, None, '0'), ('2', None, None, None), ('2', None, None, '32'), ('1', None, None, None), ('1', '2', None, None),
         ('1', '4', None, None)]
+if os.environ.get('SWEEP_SHAPES'):      # e.g. SWEEP_SHAPES=64,128,128,128,128;64,64,64,192,192
+    SHAPES = [tuple(int(v) for v in sh.split(',')) for sh in os.environ['SWEEP_SHAPES'].split(';')]
 if os.environ.get('SWEEP_CFGS'):
     CFGS = [tuple(None if v == '-' else v for v in c.split('/')) for c in os.environ['SWEEP_CFGS'].split(',')]
 trace = torch.zeros(8 * 3 * 256, dtype=torch.int64, device='cuda')
