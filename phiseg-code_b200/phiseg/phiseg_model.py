@@ -59,7 +59,7 @@ def net_config_from_experiment(exp, mode):
 
 class phiseg():
 
-    def __init__(self, exp_config, mode=None, device=None, use_cuda_graph=True, seed=1234):
+    def __init__(self, exp_config, mode=None, device=None, use_cuda_graph=True, seed=1234, data_parallel=True):
         """mode: 'fast' (bf16 tcgen05 tensor-core kernels, fp32 accumulate and fp32 normalisation statistics / losses /
         optimizer), 'parity_tc' (fp32 activations; every 32-channel-aligned convolution as three bf16 tcgen05 passes over a
         (hi, lo) operand split = fp32-accurate products on the tensor cores: meets the 1e-3 logit contract) or 'parity'
@@ -89,7 +89,8 @@ class phiseg():
         self.rank = 0
         # 'eager': grad graph -> NCCL all-reduce -> optimizer graph; 'graph': bucketed all-reduces captured inside the step
         self.dp_mode = os.environ.get('PHS_DP_MODE', 'eager')
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        # data_parallel=False: a replica that trains alone although a process group exists (no collectives at all)
+        if data_parallel and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size()
             self.rank = torch.distributed.get_rank()
             if self.world > 1:

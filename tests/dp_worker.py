@@ -43,8 +43,9 @@ def main():
     torch.distributed.all_reduce(loss_sum)
     ok = 1
     if rank == 0:
-        ref = pm.phiseg(exp, mode=mode, use_cuda_graph=False, seed=11)
-        ref.world = 1                        # same process group around, but this replica trains alone on the whole batch
+        # same process group around, but this replica trains alone on the whole batch (its constructor must not issue the
+        # weight broadcast the data-parallel replicas do: rank 1 is not there to take part)
+        ref = pm.phiseg(exp, mode=mode, use_cuda_graph=False, seed=11, data_parallel=False)
         ref.set_weights(dp.get_weights())
         l_ref = ref.training_step(x, s, lr=0.0, eps=eps)
         g_ref = ref.params.g
