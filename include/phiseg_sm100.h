@@ -13,6 +13,7 @@
  */
 #ifndef PHISEG_SM100_H
 #define PHISEG_SM100_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -38,6 +39,9 @@ typedef struct {
 int phs_version(void);
 int phs_arch(void); /* 100: built for sm_100a */
 const char* phs_last_error(void);
+/* CRC32C of a HOST buffer (continuing from crc; 0 to start): the checksum of TensorFlow checkpoint bundles, which
+ * tfwrapper/checkpoint.py reads and writes in place of tf.train.Saver (phiseg_model.py:144-148,505-525). */
+unsigned int phs_crc32c(const void* data, size_t n, unsigned int crc);
 /* 1 if the current device can run the tcgen05 kernels (compute capability 10.x), else 0 */
 int phs_device_ok(void);
 
@@ -189,6 +193,19 @@ int phs_sumsq_f32(const float* src, int64_t n, float scale, float* out, void* st
 int phs_weight_decay(const float* params, float* grads, const int64_t* segs, int nseg, float wd, float* loss_out,
                      void* stream);
 /* first-maximum argmax over the label axis of [npix, nlabels] (np.argmax in predict, phiseg_model.py:351-353) */
+/* ---- validation metrics (phiseg_model.py:558-640; utils.py:103-118 ncc, :270-320 generalised_energy_distance,
+ * :323-362 variance_ncc_dist; medpy jc / dc) ------------------------------------------------------------------
+ * masks_a [Ka][npix], masks_b [Kb][npix]: label masks, uint8 (elem_size 1) or int64 (8: the argmax output).  For every
+ * pair (i, j) and label l: inter[i][j][l] = |{a_i == l} & {b_j == l}|; count_a[i][l], count_b[j][l] = label histograms
+ * (may be NULL).  IoU (jc) = inter / (ca + cb - inter), Dice (dc) = 2 inter / (ca + cb): the host finishes GED / Dice
+ * from these few integers. */
+int phs_pairwise_label_stats(const void* masks_a, int elem_size_a, int Ka, const void* masks_b, int elem_size_b, int Kb,
+                             int64_t npix, int nlabels, int* inter, int* count_a, int* count_b, void* stream);
+/* softmax [N][npix][nlabels] (samples), gt uint8 [M][npix] (annotations).  e_ss[npix] = mean_i xent(mean_seg, s_i),
+ * e_sy[M][npix] = mean_i xent(onehot(gt_j), s_i) with xent(t, s) = -sum_l t_l log(s_l + 1e-8); sums[M][5] (double) =
+ * (sum a, sum a^2, sum v, sum v^2, sum a*v) over the pixels for a = e_ss, v = e_sy[j]: ncc_j = cov(a, v) / (std a std v). */
+int phs_ncc_maps(const float* softmax, const uint8_t* gt, int N, int M, int64_t npix, int nlabels, float* e_ss, float* e_sy,
+                 double* sums, void* stream);
 int phs_argmax_f32(const float* src, int64_t npix, int nlabels, int64_t* out, void* stream);
 
 #ifdef __cplusplus

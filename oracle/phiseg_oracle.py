@@ -508,6 +508,73 @@ class Oracle:
 
 
 # ----------------------------------------------------------------------------
+# validation metrics (utils.py:103-118, 270-362; phiseg_model.py:596-606) -- plain numpy on whole masks
+# ----------------------------------------------------------------------------
+def _mask_distance(m1, m2, label_range):
+    """1 - mean_l IoU(m1 == l, m2 == l); both empty -> IoU 1, exactly one empty -> IoU 0 (utils.py:272-292; jc of medpy)"""
+    tot = 0.0
+    for lbl in label_range:
+        a, b = (m1 == lbl), (m2 == lbl)
+        na, nb = int(a.sum()), int(b.sum())
+        if na == 0 and nb == 0:
+            tot += 1.0
+        elif na == 0 or nb == 0:
+            tot += 0.0
+        else:
+            tot += float(np.logical_and(a, b).sum()) / float(np.logical_or(a, b).sum())
+    return 1.0 - tot / len(list(label_range))
+
+
+def generalised_energy_distance(sample_arr, gt_arr, label_range):
+    """utils.py:270-320: sample_arr [N,X,Y], gt_arr [M,X,Y] label masks.  (The reference passes nlabels-1 as the
+    divisor together with label_range = range(1, nlabels), phiseg_model.py:586-588: the mean is over the foreground labels.)"""
+    N, M = sample_arr.shape[0], gt_arr.shape[0]
+    lr = list(label_range)
+    d_sy = sum(_mask_distance(sample_arr[i], gt_arr[j], lr) for i in range(N) for j in range(M))
+    d_ss = sum(_mask_distance(sample_arr[i], sample_arr[j], lr) for i in range(N) for j in range(N))
+    d_yy = sum(_mask_distance(gt_arr[i], gt_arr[j], lr) for i in range(M) for j in range(M))
+    return 2.0 / (N * M) * d_sy - d_ss / N ** 2 - d_yy / M ** 2
+
+
+def ncc(a, v):
+    """utils.py:103-118 with zero_norm=True: correlation of the standardised maps"""
+    a = np.asarray(a, np.float64).ravel()
+    v = np.asarray(v, np.float64).ravel()
+    a = (a - a.mean()) / (a.std() * a.size)
+    v = (v - v.mean()) / v.std()
+    return float(np.sum(a * v))
+
+
+def variance_ncc_dist(sample_sm, gt_onehot):
+    """utils.py:323-362: sample_sm [N,X,Y,L] softmax samples, gt_onehot [M,X,Y,L]"""
+    s = np.asarray(sample_sm, np.float64)
+    g = np.asarray(gt_onehot, np.float64)
+    logs = np.log(s + 1e-8)
+    mean_seg = s.mean(axis=0)
+    e_ss = np.mean(-np.sum(mean_seg[None] * logs, axis=-1), axis=0)
+    vals = []
+    for j in range(g.shape[0]):
+        e_sy = np.mean(-np.sum(g[j][None] * logs, axis=-1), axis=0)
+        vals.append(ncc(e_ss, e_sy))
+    return float(np.mean(vals))
+
+
+def per_label_dice(pred, gt, nlabels):
+    """phiseg_model.py:596-606 (dc of medpy): both empty -> 1, exactly one empty -> 0"""
+    out = []
+    for lbl in range(nlabels):
+        a, b = (pred == lbl), (gt == lbl)
+        na, nb = int(a.sum()), int(b.sum())
+        if na == 0 and nb == 0:
+            out.append(1.0)
+        elif na == 0 or nb == 0:
+            out.append(0.0)
+        else:
+            out.append(2.0 * float(np.logical_and(a, b).sum()) / float(na + nb))
+    return np.asarray(out)
+
+
+# ----------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d)
 # ----------------------------------------------------------------------------
 def synthetic_batch(B, H=128, W=128, nlabels=2, seed=1234):

@@ -45,6 +45,25 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
 extern "C" {
 
 int phs_version(void) { return 100; }
+
+/* CRC32C (Castagnoli) of a host buffer, continuing from `crc` (0 to start): the checksum TensorFlow checkpoint bundles and
+ * the LevelDB table format carry (tfwrapper/checkpoint.py).  Plain host code: slicing-by-1 table, ~400 MB/s. */
+unsigned int phs_crc32c(const void* data, size_t n, unsigned int crc) {
+  static unsigned int table[256];
+  static bool init = false;
+  if (!init) {
+    for (unsigned int i = 0; i < 256; ++i) {
+      unsigned int c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  unsigned int c = crc ^ 0xFFFFFFFFu;
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
 int phs_arch(void) { return 100; }
 const char* phs_last_error(void) { return g_err; }
 

@@ -30,3 +30,34 @@ def synthetic_eps(shapes, seed=1234):
     """One N(0,1) array per latent level (stands for the unseeded tf.random_normal of posteriors.py:108)."""
     rng = np.random.default_rng(seed + 77)
     return [rng.standard_normal(sh).astype(np.float32) for sh in shapes]
+
+
+class _Split:
+    """images [N,H,W] float32, labels [N,H,W,A] uint8 with the next_batch interface of data/batch_provider.py:43-67
+    (a random annotator per image, data/batch_provider.py:103-110)"""
+
+    def __init__(self, images, labels, seed):
+        self.images, self.labels = images, labels
+        self._rng = np.random.default_rng(seed)
+
+    def next_batch(self, batch_size):
+        idx = self._rng.choice(self.images.shape[0], size=batch_size, replace=self.images.shape[0] < batch_size)
+        ann = self._rng.integers(0, self.labels.shape[-1], size=batch_size)
+        x = self.images[idx][..., None].astype(np.float32)
+        s = np.stack([self.labels[i, :, :, a] for i, a in zip(idx, ann)])
+        return x, s.astype(np.uint8)
+
+
+class SyntheticLIDC:
+    """Stand-in for data/lidc_data.py: .train / .validation splits of smooth random images with `annotators` jittered
+    lesion masks each (the real LIDC-IDRI crops are not available offline)."""
+
+    def __init__(self, num_train=64, num_val=8, size=128, nlabels=2, annotators=4, seed=0):
+        def make(n, sd):
+            x, _ = synthetic_batch(n, size, size, nlabels, seed=sd)
+            labs = np.stack([synthetic_batch(n, size, size, nlabels, seed=sd)[1]] +
+                            [np.roll(synthetic_batch(n, size, size, nlabels, seed=sd)[1], shift=a, axis=1 + a % 2)
+                             for a in range(1, annotators)], axis=-1)
+            return x[..., 0], labs.astype(np.uint8)
+        self.train = _Split(*make(num_train, seed), seed=seed + 1)
+        self.validation = _Split(*make(num_val, seed + 100), seed=seed + 2)

@@ -66,6 +66,8 @@ SIGNATURES = {
     'phs_sumsq_f32': [_P, c_int64, c_float, _P, _S],
     'phs_weight_decay': [_P, _P, _P, c_int, c_float, _P, _S],
     'phs_argmax_f32': [_P, c_int64, c_int, _P, _S],
+    'phs_pairwise_label_stats': [_P, c_int, c_int, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
+    'phs_ncc_maps': [_P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
 }
 
 _lib = None
@@ -93,7 +95,7 @@ def load():
 
 
 def exported_symbols():
-    return list(SIGNATURES) + ['phs_version', 'phs_arch', 'phs_device_ok', 'phs_last_error']
+    return list(SIGNATURES) + ['phs_version', 'phs_arch', 'phs_device_ok', 'phs_last_error', 'phs_crc32c']
 
 
 def check(rc, what=''):

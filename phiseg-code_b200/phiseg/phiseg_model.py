@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from .. import engine as E
+from .. import metrics as M
 from .. import lib as L
 from .. import parallel
 from ..tf_compat import optimizer_kind
@@ -408,18 +409,99 @@ class phiseg():
         self.flush()
 
     def _do_validation(self, data, step):
-        """Reduced form of phiseg_model.py:530-701: checkpoint + validation ELBO with training=False + best-loss
-        tracking (GED/NCC/Dice metrics are a 'next' row)."""
+        """phiseg_model.py:530-660 without TensorBoard: checkpoint, batch validation losses (training=False), then the
+        full validation pass - per image validation_samples prior samples and ELBO evaluations, GED / NCC / Dice computed
+        on the device (validation_metrics) - and the four best-model savers (Dice, ELBO, GED, NCC; max_to_keep=2)."""
+        exp = self.exp_config
         self.save_weights(self.log_dir, 'model.ckpt-%d' % step)
         _prune_checkpoints(self.log_dir, 'model.ckpt', keep=1)             # tf.train.Saver(max_to_keep=1), :144
-        if hasattr(data, 'validation'):
-            x_b, s_b = data.validation.next_batch(self.exp_config.batch_size)
-            val = self.evaluate_losses(x_b, s_b)
-            logging.info('validation  step %d  loss %.4f' % (step, val['total_loss']))
+        if not hasattr(data, 'validation'):
+            return None
+        x_b, s_b = data.validation.next_batch(exp.batch_size)
+        val = self.evaluate_losses(x_b, s_b)
+        logging.info('validation  step %d  batch loss %.4f' % (step, val['total_loss']))
+        images = getattr(data.validation, 'images', None)
+        if images is None:
             if val['total_loss'] < self.best_loss:
                 self.best_loss = val['total_loss']
-                self.save_weights(self.log_dir, 'model_best_loss.ckpt-%d' % step)
-                _prune_checkpoints(self.log_dir, 'model_best_loss.ckpt', keep=2)   # saver_best_loss: max_to_keep=2, :145
+                self._save_best('model_best_loss.ckpt', step)
+            return val
+        n = images.shape[0] if exp.num_validation_images == 'all' else min(int(exp.num_validation_images), images.shape[0])
+        rng = np.random.default_rng(step)
+        dice, elbo, ged, ncc = [], [], [], []
+        t0 = time.time()
+        for ii in range(n):
+            x = np.asarray(images[ii]).reshape((1,) + tuple(exp.image_size))
+            m = self.validation_metrics(x, data.validation.labels[ii], exp.validation_samples,
+                                        annotator=int(rng.choice(list(exp.annotator_range))))
+            dice.append(m['dice']); elbo.append(m['elbo']); ged.append(m['ged']); ncc.append(m['ncc'])
+        per_structure = np.mean(np.asarray(dice), axis=0)
+        out = {'dice': float(per_structure.mean()), 'per_structure_dice': per_structure, 'elbo': float(np.mean(elbo)),
+               'ged': float(np.mean(ged)), 'ncc': float(np.nanmean(ncc)), 'images': n, 'seconds': time.time() - t0}
+        logging.info('FULL VALIDATION (%d images, %.2f s): dice %.4f  ELBO %.4f  GED %.4f  NCC %.4f'
+                     % (n, out['seconds'], out['dice'], out['elbo'], out['ged'], out['ncc']))
+        if out['dice'] >= getattr(self, 'best_dice', -np.inf):
+            self.best_dice = out['dice']
+            self._save_best('model_best_dice.ckpt', step)
+        if out['elbo'] <= self.best_loss:
+            self.best_loss = out['elbo']
+            self._save_best('model_best_loss.ckpt', step)
+        if out['ged'] <= getattr(self, 'best_ged', np.inf):
+            self.best_ged = out['ged']
+            self._save_best('model_best_ged.ckpt', step)
+        if out['ncc'] >= getattr(self, 'best_ncc', -np.inf):
+            self.best_ncc = out['ncc']
+            self._save_best('model_best_ncc.ckpt', step)
+        self.last_validation = out
+        return out
+
+    def _save_best(self, prefix, step):
+        self.save_weights(self.log_dir, '%s-%d' % (prefix, step))
+        _prune_checkpoints(self.log_dir, prefix, keep=2)                  # saver_best_*: max_to_keep=2, :145-148
+
+    def validation_metrics(self, x_img, s_gt_arr, num_samples=None, annotator=0, eps=None):
+        """One image of the reference's validation loop (phiseg_model.py:567-611).  x_img [1,H,W,C] (or [H,W,C]),
+        s_gt_arr [H,W,A]: the A annotations of the image.  num_samples prior samples (batched along N, x-only part once)
+        and num_samples ELBO evaluations against annotation `annotator`, then on the device: pairwise label
+        intersections -> generalised energy distance over the foreground labels, cross-entropy maps -> variance NCC,
+        and the Dice of the mean prediction.  Returns {'ged', 'ncc', 'dice' [nlabels], 'elbo'}."""
+        cfg, st = self.cfg, torch.cuda.current_stream().cuda_stream
+        S = int(num_samples or self.exp_config.validation_samples)
+        x = np.asarray(x_img, dtype=np.float32).reshape(1, cfg.H, cfg.W, cfg.Cx)
+        gts = np.ascontiguousarray(np.moveaxis(np.asarray(s_gt_arr), -1, 0)).astype(np.uint8)      # [A,H,W]
+        A, P, nl = gts.shape[0], cfg.H * cfg.W, cfg.nlabels
+        s = gts[annotator]
+        # ELBO with training=False on S copies of (x, s) (:574-581)
+        ev = self.evaluate_losses(np.tile(x, (S, 1, 1, 1)), np.tile(s[None], (S, 1, 1)))
+        # S prior samples: one pass, rows = samples
+        sp = self._program('sample', 1, S)
+        self._stage_x(sp, x)
+        L.check(self.lib.phs_fill_f32(sp.sm_accum.data_ptr(), sp.sm_accum.numel(), 0.0, st), 'phs_fill_f32')
+        self._draw_eps(sp, eps)
+        self._launch(sp, sp.prog.steps, 'fwd')
+        dev = self.device
+        gt_d = torch.as_tensor(gts).to(dev)
+        mean_arg = torch.empty((1, cfg.H, cfg.W), dtype=torch.int64, device=dev)
+        L.check(self.lib.phs_argmax_f32(sp.sm_accum.data_ptr(), P, nl, mean_arg.data_ptr(), st), 'phs_argmax_f32')
+        i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+        i_sy, i_ss, i_yy, i_d = i32(S, A, nl), i32(S, S, nl), i32(A, A, nl), i32(1, 1, nl)
+        c_s, c_y, c_p, c_g = i32(S, nl), i32(A, nl), i32(1, nl), i32(1, nl)
+        pls = self.lib.phs_pairwise_label_stats
+        am, sgt = sp.argmax, gt_d[annotator:annotator + 1].contiguous()
+        L.check(pls(am.data_ptr(), 8, S, gt_d.data_ptr(), 1, A, P, nl, i_sy.data_ptr(), c_s.data_ptr(), c_y.data_ptr(), st), 'phs_pairwise_label_stats')
+        L.check(pls(am.data_ptr(), 8, S, am.data_ptr(), 8, S, P, nl, i_ss.data_ptr(), None, None, st), 'phs_pairwise_label_stats')
+        L.check(pls(gt_d.data_ptr(), 1, A, gt_d.data_ptr(), 1, A, P, nl, i_yy.data_ptr(), None, None, st), 'phs_pairwise_label_stats')
+        L.check(pls(mean_arg.data_ptr(), 8, 1, sgt.data_ptr(), 1, 1, P, nl, i_d.data_ptr(), c_p.data_ptr(), c_g.data_ptr(), st), 'phs_pairwise_label_stats')
+        e_ss = torch.empty(P, dtype=torch.float32, device=dev)
+        e_sy = torch.empty((A, P), dtype=torch.float32, device=dev)
+        sums = torch.empty((A, 5), dtype=torch.float64, device=dev)
+        L.check(self.lib.phs_ncc_maps(sp.s_out_sm.data_ptr(), gt_d.data_ptr(), S, A, P, nl, e_ss.data_ptr(), e_sy.data_ptr(),
+                                      sums.data_ptr(), st), 'phs_ncc_maps')
+        self.gpu_launches += 7
+        h = [t.cpu().numpy() for t in (i_sy, i_ss, i_yy, c_s, c_y, i_d, c_p, c_g, sums)]
+        fg = range(1, nl)                                        # label_range=range(1, nlabels) (:586-588)
+        return {'ged': M.ged_from_counts(h[0], h[1], h[2], h[3], h[4], fg), 'ncc': M.ncc_from_sums(h[8], P),
+                'dice': M.dice_from_counts(h[5][0, 0], h[6][0], h[7][0]), 'elbo': ev['total_loss']}
 
     def evaluate_losses(self, x_b, s_b, eps=None):
         """loss_dict with training=False (phiseg_model.py:537-549)."""
@@ -615,17 +697,12 @@ class phiseg():
     def predict_segmentation_sample_variance_sm_cov(self, x_in, num_samples):
         """phiseg_model.py:378-403: per-pixel sum of the eigenvalues of the sample covariance of s_out_eval (all classes
         but the last, clipped to [1e-5, 1-1e-5]); like the reference it expects a single image (np.squeeze)."""
-        segms = [self._sample_logits(x_in) for _ in range(num_samples)]
-        segm_arr = np.squeeze(np.asarray(segms))          # num_samples x H x W x nlabels
-        segm_arr = segm_arr[..., :-1]
-        segm_arr = segm_arr.transpose((1, 2, 3, 0))
-        segm_arr = np.clip(segm_arr, 1e-5, 1 - (1e-5))
-        corr_mat = np.einsum('ghij,ghkj->ghik', segm_arr, segm_arr) / num_samples
-        mu_mat = np.mean(segm_arr, axis=-1)
-        outer_mu = np.einsum('ghi,ghj->ghij', mu_mat, mu_mat)
-        cov_mat = corr_mat - outer_mu
-        eig, _ = np.linalg.eig(cov_mat)
-        return np.sum(eig, axis=-1)
+        # The reference builds the per-pixel (biased) sample covariance over all classes but the last, clipped to
+        # [1e-5, 1-1e-5], and sums its eigenvalues.  The eigenvalue sum of a symmetric matrix is its trace, so the map is
+        # the sum over those classes of the per-pixel population variance - no eigendecomposition needed.
+        smp = self.generate_samples(x_in, num_samples)            # [num_samples, 1, H, W, nlabels] summed-level logits
+        v = np.clip(smp[:, 0, :, :, :-1].astype(np.float64), 1e-5, 1.0 - 1e-5)
+        return v.var(axis=0).sum(axis=-1)
 
     def predict_segmentation_sample_variance_sm_cov_bf(self, x_in, num_samples):
         """phiseg_model.py:406-430: per-pixel determinant of np.cov of the softmax samples (the reference loops over the
@@ -701,6 +778,25 @@ class phiseg():
             raise FileNotFoundError('no checkpoint of type %s in %s' % (type, log_dir))
         data = path = None
         for cand in candidates:
+            if cand.endswith('.index'):
+                # a TensorFlow-1 bundle written by the reference's tf.train.Saver (model.ckpt-N.index / .data-*)
+                from ..tfwrapper import checkpoint as tfck
+                try:
+                    sd = tfck.read_bundle(cand[:-len('.index')])
+                except Exception as e:       # noqa: BLE001
+                    logging.warning('checkpoint %s is unreadable (%s); trying an older one' % (cand, e))
+                    continue
+                self.params.load_state_dict({k: v for k, v in sd.items() if self.params.has(k)}, strict=False)
+                missing = [n for n in self.params.names() if n not in sd]
+                if missing:
+                    logging.warning('%d variables are not in %s (first: %s)' % (len(missing), cand, missing[0]))
+                if 'global_step' in sd:
+                    self.params.step = int(np.asarray(sd['global_step']).reshape(-1)[0])
+                else:
+                    tail = cand[:-len('.index')].rsplit('-', 1)[-1]
+                    self.params.step = int(tail) if tail.isdigit() else 0
+                self.params.slots = None          # (the Adam slots of a TF checkpoint live under other names; start fresh)
+                return cand
             # an unreadable newest file (e.g. written by a run that died before this code wrote atomically) falls back to
             # the next older one instead of breaking the resume
             try:
@@ -734,6 +830,11 @@ class phiseg():
             self.init_step = self.params.step
             self.continue_run = True
             logging.info('continuing from %s (step %d)' % (path, self.init_step))
+            if getattr(self.exp_config, 'continue_in_new_dir', False):
+                # the reference writes the continued run next to the old one (log_dir += '_cont', phiseg_model.py:836);
+                # opt-in here because a second restart would then look in '<log_dir>' again and restart from the old step
+                self.log_dir += '_cont'
+                os.makedirs(self.log_dir, exist_ok=True)
 
 
 def _checkpoints(log_dir, prefix):
@@ -742,13 +843,14 @@ def _checkpoints(log_dir, prefix):
     if not os.path.isdir(log_dir):
         return found
     for f in os.listdir(log_dir):
-        if f.startswith(prefix) and f.endswith('.npz') and '.tmp' not in f:
-            mid = f[len(prefix):-4]
-            if mid == '':
-                found.append((0, os.path.join(log_dir, f)))
-            elif mid.startswith('-') and mid[1:].isdigit():
-                found.append((int(mid[1:]), os.path.join(log_dir, f)))
-    return [p for _, p in sorted(found, reverse=True)]
+        for ext in ('.npz', '.index'):          # our own format, or a TensorFlow-1 bundle of the reference
+            if f.startswith(prefix) and f.endswith(ext) and '.tmp' not in f:
+                mid = f[len(prefix):-len(ext)]
+                if mid == '':
+                    found.append((0, ext == '.npz', os.path.join(log_dir, f)))
+                elif mid.startswith('-') and mid[1:].isdigit():
+                    found.append((int(mid[1:]), ext == '.npz', os.path.join(log_dir, f)))
+    return [p for _, _, p in sorted(found, reverse=True)]
 
 
 def _latest_checkpoint(log_dir, prefix):
