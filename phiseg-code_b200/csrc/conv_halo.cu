@@ -604,7 +604,10 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   const char* e_g = getenv("PHS_HALO_G");
   // at most one 128-pixel tile per SM (the 16x16 levels at batch 64): a second CTA slot would stay empty, so the one
   // CTA gets the whole shared memory = a filter ring deep enough to cover the TMA round trip
-  const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") || total_subs <= num_sms() ? 1 : 2);
+  // (round 2: inside the step the small layers of the prior and the posterior run side by side on two lanes; giving each
+  // kernel whole SMs serialised them - two CTAs per SM everywhere is 0.05-0.09 ms per step faster, PHS_HALO_CTAS=1 / the
+  // old rule "one CTA per SM when there is at most one tile per SM" stay selectable)
+  const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") ? (total_subs <= num_sms() ? 1 : 2) : 2);
   // dynamic shared memory per CTA: 228 KB per SM, 1 KB reserved + ~1.8 KB static per CTA, 1 KB alignment slack
   const int budget_all = ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896;
   const int max_cols = ctas_per_sm == 1 ? 512 : 256;
@@ -614,10 +617,20 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // fused statistics and slower with them (round 2, B=64, us: 128x128 128->128 247 -> 232 / 273 -> 317 with statistics,
   // 64x64 192->192 129 -> 124 / 163 -> 140, 128x128 32->192 172 -> 187): those layers run at 71 % tensor-pipe occupancy,
   // i.e. at 75-89 % of what cuBLAS reaches on this part, and the filter ring is no longer what holds them back.
-  // Opt-in: PHS_HALO_PAIR=1 uses pairs wherever the shape allows.
+  // INSIDE the training step, however, pairs win (tools/step_ab.py, ms per step: no pairs 12.47, pairs for launches
+  // without fused statistics 12.32, pairs everywhere 12.23): fewer filter bytes per SM leave more L2 -> SM bandwidth to
+  // the kernels of the other lanes.  Default (2): pairs for the launches WITHOUT fused statistics - with statistics the
+  // two CTAs' long epilogues gate one shared accumulator hand-back and the kernel alone is slower.  PHS_HALO_PAIR=1:
+  // everywhere, 0: nowhere.
   const char* e_pair = getenv("PHS_HALO_PAIR");
   const bool pair_ok = y->C % 32 == 0 && y->C >= 32 && total_subs >= 2;
-  bool pair = pair_ok && e_pair && atoi(e_pair) == 1;
+  // PHS_HALO_PAIR: 1 = wherever possible, 2 = only launches without fused statistics, 3 = only with;
+  // PHS_HALO_PAIR_MINC / _MINCIN: smallest Cout / Cin that uses pairs
+  const int pair_mode = e_pair ? atoi(e_pair) : 2;
+  const int pair_minc = getenv("PHS_HALO_PAIR_MINC") ? atoi(getenv("PHS_HALO_PAIR_MINC")) : 32;
+  const int pair_mincin = getenv("PHS_HALO_PAIR_MINCIN") ? atoi(getenv("PHS_HALO_PAIR_MINCIN")) : 32;
+  bool pair = pair_ok && y->C >= pair_minc && x->C >= pair_mincin &&
+              (pair_mode == 1 || (pair_mode == 2 && !stats) || (pair_mode == 3 && stats));
   const int b_bytes_full = y->C * ROW;
   int b_bytes = pair ? b_bytes_full / 2 : b_bytes_full;
   // staged TMA-store epilogue: bf16 outputs that are not accumulated onto, 32-channel granularity
@@ -680,7 +693,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   if (can_stage) {
     int nb_plain = geometry(0) ? (p.b_resident ? 1 << 20 : p.nb) : 0;
     s_plain = p.S;
-    int G = e_g ? atoi(e_g) : 64;
+    int G = e_g ? atoi(e_g) : (pair ? 32 : 64);
     if (G != 32 && (G != 64 || y->C % 64 != 0)) G = 32;
     ok = geometry(G) && (p.b_resident || p.nb >= 3 || G == 32) && ring_ok(nb_plain);
     if (!ok && G == 64) ok = geometry(32) && ring_ok(nb_plain);

@@ -127,6 +127,7 @@ def test_conv_halo_cta_pairs(call, lib, oracle, monkeypatch, N, H, W, Cin, Cout)
     xd, gyd, bd = x.cuda(), gy.cuda(), b.cuda()
     wf, wdg = shadows(w.float())
     y1 = torch.zeros(N, H, W, Cout, device='cuda')
+    monkeypatch.setenv('PHS_HALO_PAIR', '0')
     call('phs_conv2d', call.T(xd), wf, bd, call.T(y1), 3, 0, 0, lib.IMPL_TC)
     monkeypatch.setenv('PHS_HALO_PAIR', '1')
     y2 = torch.zeros(N, H, W, Cout, device='cuda')

@@ -1,0 +1,3 @@
+set -x
+mkdir -p gpurun_out/r2
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
