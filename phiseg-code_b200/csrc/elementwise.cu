@@ -1,6 +1,7 @@
 // Memory-bound kernels of the PHiSeg hot path: normalisation (batch_norm / group_norm2D) forward and backward,
 // 2x2 average pool, TF1-legacy bilinear x2 up-sampling, their adjoints, and small helpers.
 // All tensors NHWC with a pixel pitch (ld) so that channel slices of concat buffers are addressed in place.
+#include <stdlib.h>
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -187,7 +188,14 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
 
 // chunks per sample for the grid = (chunks, N) streaming kernels: the largest count whose N * chunks blocks are all
 // resident at once (`slots` = SMs x blocks per SM for the kernel's register use): a single wave, no straggler blocks
+// PHS_NORM_BPS (tuning): blocks per SM assumed by the one-wave grids of the normalisation kernels (0 = each kernel's own)
+static int norm_bps_override() {
+  const char* e = getenv("PHS_NORM_BPS");
+  return e ? atoi(e) : 0;
+}
+
 static int pick_chunks(int N, int slots, int max_chunks) {
+  if (norm_bps_override() > 0) slots = 148 * norm_bps_override();
   int chunks = slots / N;
   if (chunks > max_chunks) chunks = max_chunks;
   return chunks < 1 ? 1 : chunks;

@@ -205,7 +205,8 @@ class Params:
                     self.shadow_table[name] = (soff, soff + n)
                     rows.append([self.table[name][0], soff, soff + n, taps, shape[2], shape[3], 0])
                     soff += 2 * n
-                elif kind == 'W' and cfg.mode == 'fast' and pad_eligible(shape[0], shape[2], shape[3]):
+                elif (kind == 'W' and cfg.mode == 'fast' and pad_eligible(shape[0], shape[2], shape[3])
+                      and not os.environ.get('PHS_NO_PAD')):
                     # network-input convs: im2col'ed 1x1 form, K = 9*cin zero padded to kp (phs_im2col3x3)
                     k9 = 9 * shape[2]
                     kp = 32 if k9 <= 32 else 64
