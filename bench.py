@@ -37,8 +37,8 @@ CONFIGS = {
 }
 CPU_BATCH = 12   # phiseg/experiments/phiseg_7_5.py:38
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel's largest launch, from the
-# committed `ncu --set full` capture profiles/conv_halo_r01.txt ([0]: 300.8 MB read + 229.3 MB written)
-NCU_TRAFFIC = {'128x128 128->128 k3': 530128384}
+# committed `ncu --set full` capture profiles/conv_halo_r02.txt ([0]: 300.95 MB read + 229.40 MB written; round 1: 300.8 + 229.3)
+NCU_TRAFFIC = {'128x128 128->128 k3': 530348288}
 
 
 def measured_peaks():
@@ -326,7 +326,7 @@ def main():
             burst = json.load(open(pk)).get('bf16_tflops', burst)
         line['roofline'] = {
             'bound': 'tensor', 'achieved': fl / kt / 1e12, 'peak': burst, 'unit': 'TFLOP/s', 'frac': fl / kt / 1e12 / burst,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/conv_halo_r01.txt (ncu --set full)
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/conv_halo_r02.txt (ncu --set full)
             'traffic': NCU_TRAFFIC.get(shape),
             'kernel': 'conv_halo_kernel<64> (tcgen05 3x3 conv forward + fused norm statistics) via %s, %s, batch %d: '
                       'the largest launch of the dominant kernel of the step' % (name, shape, batch),
