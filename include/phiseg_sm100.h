@@ -97,12 +97,16 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
 /* backward of the above, three launches: sums[N][C][2] = (sum g*mask, sum g*mask*xhat) ... */
 int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, int relu, double* sums, void* stream);
-/* batch_norm (training) only: phs_norm_bwd_reduce with phs_norm_bwd_finalize folded into its last block.  sums[N][C][2]
- * and *counter must have been zeroed by the caller (the engine clears one arena per step); writes coef[N][C][2] and
- * (+)= dgamma / dbeta.  The convolution in front of a batch norm has no bias, so there is no dbias. */
+/* batch_norm (training) only, two launches instead of three: only the batch totals matter, so the reduction adds straight
+ * into totals[C][2] (doubles, zeroed by the caller - the engine clears one arena per step, no memset on the chain) ... */
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, int relu, double* sums, unsigned int* counter,
-                           float* coef, float* dgamma, float* dbeta, int accumulate, void* stream);
+                           const float* gamma, const float* beta, int relu, double* totals, void* stream);
+/* ... and the apply kernel derives its two coefficients per channel from the totals itself (same expressions and
+ * rounding as phs_norm_bwd_finalize) and writes (+)= dgamma / dbeta (may be NULL).  The convolution in front of a batch
+ * norm has no bias (tfwrapper/layers.py:126-128), so there is no dbias. */
+int phs_norm_bwd_apply_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, int relu, const double* totals, const phs_tensor* dy,
+                          float* dgamma, float* dbeta, int accumulate, void* stream);
 /* ... dgamma/dbeta (+= when accumulate) and per-(n,c) coefficients coef[N][C][2]; dbias (may be NULL) is the
  * gradient of the conv bias that precedes the norm, derived analytically from the forward statistics ... */
 int phs_norm_bwd_finalize(const double* sums, const double* stats, const float* mean, const float* rstd,

@@ -17,14 +17,6 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// optional batch-norm backward finalize fused into norm_bwd_reduce_kernel (counter == nullptr: plain reduce)
-struct BwdFin {
-  unsigned int* counter;   // zeroed by the caller; one ticket per block
-  float* coef;             // [N][C][2]
-  float* dgamma;
-  float* dbeta;
-  int accumulate;
-};
 
 template <typename T, int V>
 __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __restrict__ y, int HW, int C, int ld,
@@ -76,13 +68,13 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
   }
 }
 
-// sums[n][c] = (sum g*mask, sum g*mask*xhat)
+// sums[n][c] = (sum g*mask, sum g*mask*xhat); per_sample == 0: sums[c] = the same summed over the batch
 template <typename T, int V>
 __global__ void __launch_bounds__(RED_THREADS, 3)
     norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                           double* __restrict__ sums, BwdFin fin) {
+                           double* __restrict__ sums, int per_sample) {
   PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
@@ -148,41 +140,8 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
   for (int i = threadIdx.x; i < C * 2; i += RED_THREADS) {
     float a = 0.f;
     for (int l = 0; l < PL; ++l) a += sm[(size_t)l * C * 2 + i];
-    atomicAdd(&sums[(size_t)n * C * 2 + i], (double)a);
-  }
-  if (fin.counter == nullptr) return;
-  // fused batch-norm finalize: the block that arrives last sees every block's sums and turns them into the apply
-  // coefficients and the gamma / beta gradients (saves a launch and a memset on the backward chain of every layer)
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(fin.counter, 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // one THREAD per channel (coalesced over c, the N loads of a thread are independent): a warp per channel would
-  // serialise C / 8 dependent L2 round trips in this single block (measured: +20 us per layer)
-  const int N = gridDim.y;
-  for (int c = threadIdx.x; c < C; c += RED_THREADS) {
-    double a1 = 0.0, a2 = 0.0;
-    int nn = 0;
-    for (; nn + 8 <= N; nn += 8) {
-      double2 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const double2*>(sums) + (size_t)(nn + u) * C + c);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { a1 += v[u].x; a2 += v[u].y; }
-    }
-    for (; nn < N; ++nn) {
-      const double2 v = __ldcg(reinterpret_cast<const double2*>(sums) + (size_t)nn * C + c);
-      a1 += v.x; a2 += v.y;
-    }
-    const double cnt = (double)HW * N;
-    const float ga1 = gamma[c];
-    const float2 m = make_float2((float)(ga1 * a1 / cnt), (float)(ga1 * a2 / cnt));
-    for (nn = 0; nn < N; ++nn) reinterpret_cast<float2*>(fin.coef)[(size_t)nn * C + c] = m;
-    if (fin.dgamma) fin.dgamma[c] = (fin.accumulate ? fin.dgamma[c] : 0.f) + (float)a2;
-    if (fin.dbeta) fin.dbeta[c] = (fin.accumulate ? fin.dbeta[c] : 0.f) + (float)a1;
+    // per_sample == 0 (training-mode batch norm): only the batch totals [C][2] are needed downstream
+    atomicAdd(&sums[(per_sample ? (size_t)n * C * 2 : 0) + i], (double)a);
   }
 }
 
@@ -249,14 +208,13 @@ int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* m
   PHS_DISPATCH_DTYPE(y->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
-                                                rstd, gamma, beta, relu, sums, BwdFin{nullptr, nullptr, nullptr, nullptr, 0}))));
+                                                rstd, gamma, beta, relu, sums, 1))));
   return phs_check_launch("norm_bwd_reduce");
 }
 
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                           const float* gamma, const float* beta, int relu, double* sums, unsigned int* counter,
-                           float* coef, float* dgamma, float* dbeta, int accumulate, void* stream) {
-  PHS_REQUIRE(g && y && g->ptr && y->ptr && sums && counter && coef, "phs_norm_bwd_reduce_bn: null argument");
+                           const float* gamma, const float* beta, int relu, double* totals, void* stream) {
+  PHS_REQUIRE(g && y && g->ptr && y->ptr && totals, "phs_norm_bwd_reduce_bn: null argument");
   PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C,
               "phs_norm_bwd_reduce_bn: g/y mismatch");
   cudaStream_t st = (cudaStream_t)stream;
@@ -265,18 +223,12 @@ int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float
   dim3 grid; int ppb; size_t smem;
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce_bn: C=%d too large", y->C);
-  const BwdFin fin{counter, coef, dgamma, dbeta, accumulate};
   PHS_DISPATCH_DTYPE(y->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
-                                                rstd, gamma, beta, relu, sums, fin))));
+                                                rstd, gamma, beta, relu, totals, 0))));
   return phs_check_launch("norm_bwd_reduce_bn");
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// finalize kernels (tiny): one thread per channel (BN) or per (n, channel) (GN)
-// ---------------------------------------------------------------------------------------------------------
-// one WARP per channel (BN: lanes stride over the samples) or one thread per (n, c) (GN)
 
 __global__ void __launch_bounds__(128) norm_finalize_kernel(const double* __restrict__ stats, int N, int HW, int C,
                                                             int mode, float eps, float decay, float* moving_mean,
@@ -620,12 +572,22 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
   return phs_check_launch("norm_act_fwd");
 }
 
+// batch-norm shortcut of norm_bwd_apply_kernel: batch totals [C][2] from phs_norm_bwd_reduce_bn instead of coef[N][C][2]
+struct BnTotals {
+  const double* totals;   // nullptr: use coef
+  double count;           // N * H * W
+  float* dgamma;
+  float* dbeta;
+  int accumulate;
+};
+
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 3)
     norm_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dy,
                           int lddy, int HW, int C, int pix_per_block, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, int relu, const float* __restrict__ coef) {
+                          const float* __restrict__ beta, int relu, const float* __restrict__ coef,
+                          BnTotals bn) {
   PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
@@ -650,8 +612,20 @@ __global__ void __launch_bounds__(256, 3)
       sc[k] = gamma[c] * rs[k];
       sh[k] = beta[c] + gamma[c] * xo[k];
       gr[k] = gamma[c] * rs[k];
-      k1[k] = rs[k] * coef[nc * 2];
-      k2[k] = rs[k] * coef[nc * 2 + 1];
+      if (bn.totals) {
+        // training-mode batch norm: the finalize step is two multiplications per channel, done here from the batch
+        // totals (same expressions and rounding as norm_bwd_finalize_kernel); block (0, 0) also owns dgamma / dbeta
+        const double a1 = bn.totals[2 * c], a2 = bn.totals[2 * c + 1];
+        k1[k] = rs[k] * (float)(gamma[c] * a1 / bn.count);
+        k2[k] = rs[k] * (float)(gamma[c] * a2 / bn.count);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && lane_p == 0) {
+          if (bn.dgamma) bn.dgamma[c] = (bn.accumulate ? bn.dgamma[c] : 0.f) + (float)a2;
+          if (bn.dbeta) bn.dbeta[c] = (bn.accumulate ? bn.dbeta[c] : 0.f) + (float)a1;
+        }
+      } else {
+        k1[k] = rs[k] * coef[nc * 2];
+        k2[k] = rs[k] * coef[nc * 2 + 1];
+      }
     }
     int p = p0 + lane_p;
     for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
@@ -689,22 +663,37 @@ __global__ void __launch_bounds__(256, 3)
   }
 }
 
-int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                       const float* gamma, const float* beta, int relu, const float* coef, const phs_tensor* dy,
-                       void* stream) {
-  PHS_REQUIRE(g && y && dy && g->ptr && y->ptr && dy->ptr && coef, "phs_norm_bwd_apply: null argument");
+static int norm_bwd_apply_run(const char* what, const phs_tensor* g, const phs_tensor* y, const float* mean,
+                              const float* rstd, const float* gamma, const float* beta, int relu, const float* coef,
+                              BnTotals bn, const phs_tensor* dy, void* stream) {
+  PHS_REQUIRE(g && y && dy && g->ptr && y->ptr && dy->ptr && (coef || bn.totals), "%s: null argument", what);
   PHS_REQUIRE(g->dtype == y->dtype && dy->dtype == y->dtype && g->C == y->C && dy->C == y->C && g->N == y->N &&
                   g->H == y->H && g->W == y->W,
-              "phs_norm_bwd_apply: tensor mismatch");
+              "%s: tensor mismatch", what);
   int v = min_vec(min_vec(pick_vec(y), pick_vec(g)), pick_vec(dy));
   int HW = y->H * y->W;
+  bn.count = (double)HW * y->N;
   dim3 grid; int ppb;
   stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);
   PHS_DISPATCH_DTYPE(y->dtype, T,
                      PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_apply_kernel<T, V>, grid, 256, 0, (cudaStream_t)stream, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
-                                                HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef))));
-  return phs_check_launch("norm_bwd_apply");
+                                                HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef, bn))));
+  return phs_check_launch(what);
+}
+
+int phs_norm_bwd_apply(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, const float* coef, const phs_tensor* dy,
+                       void* stream) {
+  return norm_bwd_apply_run("phs_norm_bwd_apply", g, y, mean, rstd, gamma, beta, relu, coef,
+                            BnTotals{nullptr, 0.0, nullptr, nullptr, 0}, dy, stream);
+}
+
+int phs_norm_bwd_apply_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta, int relu, const double* totals, const phs_tensor* dy,
+                          float* dgamma, float* dbeta, int accumulate, void* stream) {
+  return norm_bwd_apply_run("phs_norm_bwd_apply_bn", g, y, mean, rstd, gamma, beta, relu, nullptr,
+                            BnTotals{totals, 0.0, dgamma, dbeta, accumulate}, dy, stream);
 }
 
 // ---- 2x2 average pool ------------------------------------------------------------------------------------

@@ -638,24 +638,25 @@ class Builder:
                 if nb is not None:
                     mode, stats, mean, rstd, gamma, beta, dgamma, dbeta = nb
                     N, HW, C = x.N, x.H * x.W, cout
-                    sums, coef = pr.dvec(N * C * 2), pr.vec(N * C * 2)
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
-                    if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_FUSED_BN_BWD'):
-                        # reduce + finalize in one launch (sums and the block ticket in the pre-cleared arena).  Measured
-                        # neutral-to-slower (13.21 vs 13.17 ms per step: the last block's tail costs what the launch did),
-                        # so it stays opt-in
-                        sums = pr.stats_vec(N * C * 2 + 32)
+                    if mode == L.NORM_BN_TRAIN and dbias is None and not os.environ.get('PHS_BN_BWD3'):
+                        # batch norm: two launches.  The reduction adds into batch totals that live in the arena the
+                        # program clears once, and the apply kernel derives its coefficients (and dgamma / dbeta) from
+                        # them - no memset node and no 5-us finalize launch on the backward chain of every layer
+                        tot = pr.stats_vec(C * 2)
                         self.emit('phs_norm_bwd_reduce_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
-                                  beta, int(relu), sums.data_ptr(), sums.data_ptr() + 8 * N * C * 2, coef.data_ptr(),
-                                  dgamma, dbeta, 1)
+                                  beta, int(relu), tot.data_ptr())
+                        self.emit('phs_norm_bwd_apply_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
+                                  beta, int(relu), tot.data_ptr(), dy.desc(), dgamma, dbeta, 1)
                     else:
+                        sums, coef = pr.dvec(N * C * 2), pr.vec(N * C * 2)
                         self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
                                   beta, int(relu), sums.data_ptr())
                         self.emit('phs_norm_bwd_finalize', sums.data_ptr(), stats.data_ptr(), mean.data_ptr(),
                                   rstd.data_ptr(), gamma, N, HW, C, mode, coef.data_ptr(), dgamma, dbeta, dbias, 1)
-                    self.emit('phs_norm_bwd_apply', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
-                              int(relu), coef.data_ptr(), dy.desc())
+                        self.emit('phs_norm_bwd_apply', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
+                                  int(relu), coef.data_ptr(), dy.desc())
                     db = None
                 else:
                     dy = ga

@@ -40,7 +40,8 @@ SIGNATURES = {
     'phs_norm_act_fwd': [_T, _P, _P, _P, _P, c_int, _T, _S],
     'phs_norm_act_fwd_stats': [_T, _P, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_int, _T, _S],
     'phs_norm_bwd_reduce': [_T, _T, _P, _P, _P, _P, c_int, _P, _S],
-    'phs_norm_bwd_reduce_bn': [_T, _T, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_int, _S],
+    'phs_norm_bwd_reduce_bn': [_T, _T, _P, _P, _P, _P, c_int, _P, _S],
+    'phs_norm_bwd_apply_bn': [_T, _T, _P, _P, _P, _P, c_int, _P, _T, _P, _P, c_int, _S],
     'phs_norm_bwd_finalize': [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _S],
     'phs_norm_bwd_apply': [_T, _T, _P, _P, _P, _P, c_int, _P, _T, _S],
     'phs_avgpool2_fwd': [_T, _T, _S],

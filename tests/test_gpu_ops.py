@@ -176,16 +176,17 @@ def test_norm_fwd_bwd(call, lib, oracle, mode, shape):
     close(dbias, y.grad.sum(dim=(0, 1, 2)), rtol=1e-3, atol=1e-3 * float(y.grad.abs().sum(dim=(0, 1, 2)).max()) + 1e-5,
           what='dbias')
     if mode == 'bn_train':
-        # fused variant: the last block of the reduction does the finalize (pre-zeroed sums + ticket counter)
-        buf = torch.zeros(N * C * 2 + 32, device='cuda', dtype=torch.float64)
-        coef2 = torch.empty(N * C * 2, device='cuda')
-        dgam2 = torch.zeros(C, device='cuda')
-        dbet2 = torch.zeros(C, device='cuda')
-        call('phs_norm_bwd_reduce_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, buf, buf.data_ptr() + 8 * N * C * 2,
-             coef2, dgam2, dbet2, 1)
-        close(coef2, coef.double().cpu(), rtol=1e-5, what='fused coef')
-        close(dgam2, gamma.grad, rtol=2e-4, what='fused dgamma')
-        close(dbet2, beta.grad, rtol=2e-4, what='fused dbeta')
+        # two-launch batch-norm variant: totals-only reduction onto a cleared buffer, finalize folded into the apply
+        tot = torch.zeros(C * 2, device='cuda', dtype=torch.float64)
+        dgam2 = torch.full((C,), 0.5, device='cuda')
+        dbet2 = torch.full((C,), -0.25, device='cuda')
+        dyd2 = torch.empty_like(yd)
+        call('phs_norm_bwd_reduce_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, tot)
+        close(tot, sums.view(N, C, 2).sum(dim=0).reshape(-1).cpu(), rtol=1e-6, what='batch totals')
+        call('phs_norm_bwd_apply_bn', call.T(gad), call.T(yd), mean, rstd, gd, bd, 1, tot, call.T(dyd2), dgam2, dbet2, 1)
+        assert torch.equal(dyd2, dyd), 'two-launch batch-norm backward differs from the three-launch one'
+        close(dgam2 - 0.5, gamma.grad, rtol=2e-4, what='dgamma (accumulated onto 0.5)')
+        close(dbet2 + 0.25, beta.grad, rtol=2e-4, what='dbeta (accumulated onto -0.25)')
 
 
 # ---------------------------------------------------------------------------------------------------------
