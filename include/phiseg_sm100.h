@@ -211,6 +211,17 @@ int phs_pairwise_label_stats(const void* masks_a, int elem_size_a, int Ka, const
 int phs_ncc_maps(const float* softmax, const uint8_t* gt, int N, int M, int64_t npix, int nlabels, float* e_ss, float* e_sy,
                  double* sums, void* stream);
 int phs_argmax_f32(const float* src, int64_t npix, int nlabels, int64_t* out, void* stream);
+/* Uncertainty maps of phiseg_model.py:378-475 without stacking the samples on the host.  logits [S][B][npix][nlabels]
+ * (one batched sampling pass, row = s*B + b), gt uint8 [B][npix] or NULL.  Per image pixel, acc (doubles, cleared by the
+ * caller, [B*npix][nl + nl(nl+1)/2 + 1]) += (sum_s v_c | sum_s v_i v_j for i <= j | sum_s cross entropy of the logits
+ * against gt), where v = softmax(logits) (kind 0: s_out_eval_sm) or clip(logits, lo, hi) (kind 1: :390). */
+int phs_sample_moments(const float* logits, const uint8_t* gt, int S, int B, int64_t npix, int nlabels, int kind, float lo,
+                       float hi, double* acc, void* stream);
+/* ... and the maps from `count` accumulated samples (every output may be NULL): mean_arg = argmax_c of the mean (:470),
+ * std_mean = mean_c np.std (:467-468), var_sum = trace of the covariance of the first nlabels - drop_last classes (the
+ * eigenvalue sum of :393-402), cov_det = det(np.cov) of all classes (:423-428), err = mean cross entropy (:444-446,472). */
+int phs_sample_maps(const double* acc, int64_t total_pix, int nlabels, int count, int drop_last, int64_t* mean_arg,
+                    float* std_mean, float* var_sum, float* cov_det, float* err, void* stream);
 
 #ifdef __cplusplus
 }

@@ -575,6 +575,52 @@ def per_label_dice(pred, gt, nlabels):
 
 
 # ----------------------------------------------------------------------------
+# uncertainty maps (phiseg_model.py:378-475) -- numpy on stacked samples of ONE image, as the reference computes them
+# ----------------------------------------------------------------------------
+def _softmax_np(logits):
+    z = np.asarray(logits, np.float64)
+    e = np.exp(z - z.max(axis=-1, keepdims=True))
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+def _xent_np(logits, gt):
+    """tf.nn.softmax_cross_entropy_with_logits against one_hot(gt) (phiseg_model.py:304-311): logsumexp - logit[gt]"""
+    z = np.asarray(logits, np.float64)
+    m = z.max(axis=-1, keepdims=True)
+    lse = np.log(np.exp(z - m).sum(axis=-1)) + m[..., 0]
+    return lse - np.take_along_axis(z, np.asarray(gt)[..., None].astype(np.int64), axis=-1)[..., 0]
+
+
+def sample_variance_sm_cov(logit_samples):
+    """phiseg_model.py:386-403: logit_samples [S,X,Y,L] (s_out_eval of S prior samples of one image)"""
+    segm = np.asarray(logit_samples, np.float64)[..., :-1].transpose((1, 2, 3, 0))
+    segm = np.clip(segm, 1e-5, 1 - 1e-5)
+    n = segm.shape[-1]
+    corr = np.einsum('ghij,ghkj->ghik', segm, segm) / n
+    mu = segm.mean(axis=-1)
+    cov = corr - np.einsum('ghi,ghj->ghij', mu, mu)
+    ev, _ = np.linalg.eig(cov)
+    return np.sum(ev, axis=-1).real
+
+
+def sample_variance_sm_cov_bf(logit_samples):
+    """phiseg_model.py:414-430: per-pixel det(np.cov) of the softmax samples"""
+    sm = _softmax_np(logit_samples).transpose((1, 2, 3, 0))
+    out = np.zeros(sm.shape[:2])
+    for i in range(sm.shape[0]):
+        for j in range(sm.shape[1]):
+            out[i, j] = np.linalg.det(np.cov(sm[i, j]))
+    return out
+
+
+def mean_variance_and_error_maps(logit_samples, gt):
+    """phiseg_model.py:458-475: (argmax of the mean softmax, class-mean of np.std over the samples, mean cross entropy)"""
+    sm = _softmax_np(logit_samples)
+    errs = np.stack([_xent_np(z, gt) for z in np.asarray(logit_samples)])
+    return np.argmax(sm.mean(axis=0), axis=-1), np.std(sm, axis=0).mean(axis=-1), errs.mean(axis=0)
+
+
+# ----------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d)
 # ----------------------------------------------------------------------------
 def synthetic_batch(B, H=128, W=128, nlabels=2, seed=1234):

@@ -116,6 +116,121 @@ __global__ void __launch_bounds__(256) ncc_reduce_kernel(const float* __restrict
   }
 }
 
+// Uncertainty maps (phiseg_model.py:378-475): the reference stacks num_samples full-resolution outputs on the host and
+// takes per-pixel moments with numpy.  Here every sampling pass (S rows per image, row = s*B + b) adds, per image pixel,
+//   acc[0 .. nl)              sum_s v_c
+//   acc[nl .. nl + nl(nl+1)/2) sum_s v_i v_j  (i <= j, row-major upper triangle)
+//   acc[last]                 sum_s xent(logits_s, gt)         (softmax_cross_entropy_with_logits, :304-311)
+// into doubles; v = softmax(logits) (kind 0) or the raw summed logits clipped to [lo, hi] (kind 1, :390).
+__device__ __forceinline__ int tri_index(int i, int j, int nl) { return i * nl - i * (i - 1) / 2 + (j - i); }
+
+__global__ void __launch_bounds__(256) sample_moments_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ gt,
+                                                             int S, int B, int64_t P, int nl, int kind, float lo, float hi,
+                                                             double* __restrict__ acc) {
+  const int na = nl + nl * (nl + 1) / 2 + 1;
+  const int64_t total = (int64_t)B * P;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    double s1[MET_MAXL], s2[MET_MAXL * (MET_MAXL + 1) / 2], xe = 0.0;
+#pragma unroll
+    for (int l = 0; l < MET_MAXL; ++l) s1[l] = 0.0;
+#pragma unroll
+    for (int l = 0; l < MET_MAXL * (MET_MAXL + 1) / 2; ++l) s2[l] = 0.0;
+    const int lab = gt ? (int)gt[q] : -1;
+    for (int s = 0; s < S; ++s) {
+      const float* r = logits + ((int64_t)s * total + q) * nl;
+      float v[MET_MAXL], mx = -3.0e38f;
+#pragma unroll
+      for (int l = 0; l < MET_MAXL; ++l)
+        if (l < nl) { v[l] = r[l]; mx = fmaxf(mx, v[l]); }
+      float den = 0.f, vl = 0.f;
+#pragma unroll
+      for (int l = 0; l < MET_MAXL; ++l)
+        if (l < nl) {
+          den += expf(v[l] - mx);
+          if (l == lab) vl = v[l];
+        }
+      if (lab >= 0) xe += (double)(logf(den) + mx - vl);
+#pragma unroll
+      for (int l = 0; l < MET_MAXL; ++l)
+        if (l < nl) v[l] = kind == 0 ? expf(v[l] - mx) / den : fminf(fmaxf(v[l], lo), hi);
+#pragma unroll
+      for (int i = 0; i < MET_MAXL; ++i)
+        if (i < nl) {
+          s1[i] += (double)v[i];
+#pragma unroll
+          for (int j = i; j < MET_MAXL; ++j)       // register triangle indexed for MET_MAXL: static after unrolling
+            if (j < nl) s2[tri_index(i, j, MET_MAXL)] += (double)v[i] * (double)v[j];
+        }
+    }
+    double* a = acc + q * na;
+#pragma unroll
+    for (int i = 0; i < MET_MAXL; ++i)
+      if (i < nl) {
+        a[i] += s1[i];
+#pragma unroll
+        for (int j = i; j < MET_MAXL; ++j)
+          if (j < nl) a[nl + tri_index(i, j, nl)] += s2[tri_index(i, j, MET_MAXL)];
+      }
+    a[na - 1] += xe;
+  }
+}
+
+// maps from the accumulated moments of `count` samples; every output pointer may be NULL
+//   mean_arg  argmax_c mean_s v_c                                              (:470)
+//   std_mean  mean_c sqrt(population variance of v_c)                           (:467-468, np.std)
+//   var_sum   sum over the first nl - drop_last classes of the population variance = trace of the covariance (:393-402)
+//   cov_det   determinant of the unbiased sample covariance of all classes      (:423-428, np.cov)
+//   err       mean_s xent                                                       (:444-446, :472)
+__global__ void __launch_bounds__(256) sample_maps_kernel(const double* __restrict__ acc, int64_t total, int nl, int count,
+                                                          int drop_last, int64_t* __restrict__ mean_arg,
+                                                          float* __restrict__ std_mean, float* __restrict__ var_sum,
+                                                          float* __restrict__ cov_det, float* __restrict__ err) {
+  const int na = nl + nl * (nl + 1) / 2 + 1;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const double* a = acc + q * na;
+    const double inv = 1.0 / (double)count;
+    double m[MET_MAXL];
+    int best = 0;
+    for (int l = 0; l < nl; ++l) {
+      m[l] = a[l] * inv;
+      if (m[l] > m[best]) best = l;
+    }
+    if (mean_arg) mean_arg[q] = best;
+    double sd = 0.0, vs = 0.0;
+    for (int l = 0; l < nl; ++l) {
+      const double var = fmax(a[nl + tri_index(l, l, nl)] * inv - m[l] * m[l], 0.0);
+      sd += sqrt(var);
+      if (l < nl - drop_last) vs += var;
+    }
+    if (std_mean) std_mean[q] = (float)(sd / nl);
+    if (var_sum) var_sum[q] = (float)vs;
+    if (err) err[q] = (float)(a[na - 1] * inv);
+    if (cov_det) {
+      double c[MET_MAXL][MET_MAXL];
+      const double un = 1.0 / (double)(count > 1 ? count - 1 : 1);
+      for (int i = 0; i < nl; ++i)
+        for (int j = i; j < nl; ++j) c[i][j] = c[j][i] = (a[nl + tri_index(i, j, nl)] - (double)count * m[i] * m[j]) * un;
+      double det = 1.0;      // Gaussian elimination with partial pivoting (what LAPACK's getrf does for np.linalg.det)
+      for (int k = 0; k < nl; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < nl; ++i)
+          if (fabs(c[i][k]) > fabs(c[piv][k])) piv = i;
+        if (c[piv][k] == 0.0) { det = 0.0; break; }
+        if (piv != k) {
+          for (int j = 0; j < nl; ++j) { const double t = c[k][j]; c[k][j] = c[piv][j]; c[piv][j] = t; }
+          det = -det;
+        }
+        det *= c[k][k];
+        for (int i = k + 1; i < nl; ++i) {
+          const double f = c[i][k] / c[k][k];
+          for (int j = k; j < nl; ++j) c[i][j] -= f * c[k][j];
+        }
+      }
+      cov_det[q] = (float)det;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -140,6 +255,28 @@ int phs_ncc_maps(const float* softmax, const uint8_t* gt, int N, int M, int64_t 
   ncc_maps_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(softmax, gt, N, M, npix, nlabels, e_ss, e_sy);
   ncc_reduce_kernel<<<M, 256, 0, (cudaStream_t)stream>>>(e_ss, e_sy, npix, sums);
   return phs_check_launch("ncc_maps");
+}
+
+int phs_sample_moments(const float* logits, const uint8_t* gt, int S, int B, int64_t npix, int nlabels, int kind, float lo,
+                       float hi, double* acc, void* stream) {
+  PHS_REQUIRE(logits && acc, "phs_sample_moments: null argument");
+  PHS_REQUIRE(nlabels >= 1 && nlabels <= MET_MAXL && S >= 1 && B >= 1 && npix >= 1, "phs_sample_moments: bad sizes");
+  PHS_REQUIRE(kind == 0 || kind == 1, "phs_sample_moments: kind must be 0 (softmax) or 1 (clipped logits)");
+  const int64_t total = (int64_t)B * npix;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  sample_moments_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(logits, gt, S, B, npix, nlabels, kind, lo, hi, acc);
+  return phs_check_launch("sample_moments");
+}
+
+int phs_sample_maps(const double* acc, int64_t total_pix, int nlabels, int count, int drop_last, int64_t* mean_arg,
+                    float* std_mean, float* var_sum, float* cov_det, float* err, void* stream) {
+  PHS_REQUIRE(acc, "phs_sample_maps: null argument");
+  PHS_REQUIRE(nlabels >= 1 && nlabels <= MET_MAXL && count >= 1 && total_pix >= 1 && drop_last >= 0 && drop_last < nlabels,
+              "phs_sample_maps: bad sizes");
+  const int blocks = (int)((total_pix + 255) / 256 < 148 * 8 ? (total_pix + 255) / 256 : 148 * 8);
+  sample_maps_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(acc, total_pix, nlabels, count, drop_last, mean_arg, std_mean,
+                                                              var_sum, cov_det, err);
+  return phs_check_launch("sample_maps");
 }
 
 }  // extern "C"

@@ -69,6 +69,8 @@ SIGNATURES = {
     'phs_argmax_f32': [_P, c_int64, c_int, _P, _S],
     'phs_pairwise_label_stats': [_P, c_int, c_int, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
     'phs_ncc_maps': [_P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
+    'phs_sample_moments': [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _S],
+    'phs_sample_maps': [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _S],
 }
 
 _lib = None

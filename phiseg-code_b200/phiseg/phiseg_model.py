@@ -686,55 +686,54 @@ class phiseg():
         nearest-neighbour resized to the image size (likelihoods.py:221)."""
         return self.predict_segmentation_sample_levels(x_in, return_softmax=False)
 
-    def _sample_logits(self, x_in, softmax=False):
-        """One evaluation of s_out_eval (summed level logits) or s_out_eval_sm of a prior sample: [B,H,W,nlabels]."""
-        B = int(np.shape(x_in)[0])
-        sp = self._program('sample', B)
-        self._stage_x(sp, x_in)
-        self._sample_once(sp)
-        return self._np(sp.s_out_sm if softmax else sp.s_out)
+    def _sample_maps(self, x_in, num_samples, s_gt=None, kind=0, drop_last=0, want=('mean_arg',)):
+        """Per-pixel moments of num_samples prior samples, accumulated on the device (phs_sample_moments after every
+        batched sampling pass: class sums, class cross products, cross entropy against s_gt) and turned into the requested
+        maps by phs_sample_maps.  kind 0: moments of softmax(s_out); kind 1: of s_out clipped to [1e-5, 1-1e-5]
+        (phiseg_model.py:390).  Returns {name: numpy [B,H,W]}; only the maps leave the device."""
+        cfg, st = self.cfg, torch.cuda.current_stream().cuda_stream
+        B, P, nl = int(np.shape(x_in)[0]), cfg.H * cfg.W, cfg.nlabels
+        na = nl + nl * (nl + 1) // 2 + 1
+        acc = torch.zeros(B * P * na, dtype=torch.float64, device=self.device)
+        gt = None
+        if s_gt is not None:
+            s = np.asarray(s_gt).reshape(B, cfg.H, cfg.W)
+            self._check_labels(s)
+            gt = torch.as_tensor(np.ascontiguousarray(s.astype(np.uint8))).to(self.device)
+
+        def visit(sp):
+            L.check(self.lib.phs_sample_moments(sp.s_out.data_ptr(), gt.data_ptr() if gt is not None else None, sp.rep, B, P,
+                                                nl, kind, 1e-5, 1.0 - 1e-5, acc.data_ptr(), st), 'phs_sample_moments')
+            self.gpu_launches += 1
+        self._run_samples(x_in, num_samples, visit=visit)
+        out = {k: torch.empty((B, cfg.H, cfg.W), dtype=torch.int64 if k == 'mean_arg' else torch.float32, device=self.device)
+               for k in want}
+        ptr = lambda k: out[k].data_ptr() if k in out else None
+        L.check(self.lib.phs_sample_maps(acc.data_ptr(), B * P, nl, int(num_samples), drop_last, ptr('mean_arg'),
+                                         ptr('std_mean'), ptr('var_sum'), ptr('cov_det'), ptr('err'), st), 'phs_sample_maps')
+        self.gpu_launches += 1
+        return {k: self._np(v) for k, v in out.items()}
 
     def predict_segmentation_sample_variance_sm_cov(self, x_in, num_samples):
-        """phiseg_model.py:378-403: per-pixel sum of the eigenvalues of the sample covariance of s_out_eval (all classes
-        but the last, clipped to [1e-5, 1-1e-5]); like the reference it expects a single image (np.squeeze)."""
-        # The reference builds the per-pixel (biased) sample covariance over all classes but the last, clipped to
-        # [1e-5, 1-1e-5], and sums its eigenvalues.  The eigenvalue sum of a symmetric matrix is its trace, so the map is
-        # the sum over those classes of the per-pixel population variance - no eigendecomposition needed.
-        smp = self.generate_samples(x_in, num_samples)            # [num_samples, 1, H, W, nlabels] summed-level logits
-        v = np.clip(smp[:, 0, :, :, :-1].astype(np.float64), 1e-5, 1.0 - 1e-5)
-        return v.var(axis=0).sum(axis=-1)
+        """phiseg_model.py:378-403: per-pixel sum of the eigenvalues of the (biased) sample covariance of s_out_eval over
+        all classes but the last, clipped to [1e-5, 1-1e-5].  The eigenvalue sum of a symmetric matrix is its trace, so the
+        map is the sum of the per-class population variances; like the reference it expects a single image."""
+        return self._sample_maps(x_in, num_samples, kind=1, drop_last=1, want=('var_sum',))['var_sum'][0].astype(np.float64)
 
     def predict_segmentation_sample_variance_sm_cov_bf(self, x_in, num_samples):
-        """phiseg_model.py:406-430: per-pixel determinant of np.cov of the softmax samples (the reference loops over the
-        pixels; the batched form below computes the same unbiased covariance and determinant)."""
-        segms = [self._sample_logits(x_in, softmax=True) for _ in range(num_samples)]
-        segm_arr = np.squeeze(np.asarray(segms)).transpose((1, 2, 3, 0)).astype(np.float64)   # H, W, nlabels, samples
-        xc = segm_arr - segm_arr.mean(axis=-1, keepdims=True)
-        cov = np.einsum('ghis,ghjs->ghij', xc, xc) / max(num_samples - 1, 1)
-        return np.linalg.det(cov)
+        """phiseg_model.py:406-430: per-pixel determinant of np.cov of the softmax samples (a python loop over the pixels
+        in the reference; one thread per pixel here)."""
+        return self._sample_maps(x_in, num_samples, kind=0, want=('cov_det',))['cov_det'][0].astype(np.float64)
 
     def get_crossentropy_error_map(self, s_gt, x_in, num_samples=100):
-        """phiseg_model.py:433-446: mean over samples of the per-pixel cross entropy of s_out_eval."""
-        s = np.asarray(s_gt).astype(np.int64)
-        acc = 0.0
-        for _ in range(num_samples):
-            sm = self.predict_segmentation_sample(x_in, return_softmax=True)
-            p = np.take_along_axis(sm, s[..., None], axis=-1)[..., 0]
-            acc = acc - np.log(np.maximum(p, 1e-38))
-        return acc / num_samples
+        """phiseg_model.py:433-446: mean over samples of eval_xent, the per-pixel cross entropy of s_out_eval: [B,H,W]."""
+        return self._sample_maps(x_in, num_samples, s_gt=s_gt, want=('err',))['err']
 
     def predict_mean_variance_and_error_maps(self, s_gt, x_in, num_samples):
-        """phiseg_model.py:449-475"""
-        s = np.asarray(s_gt).astype(np.int64)
-        segs, errs = [], []
-        for _ in range(num_samples):
-            sm = self.predict_segmentation_sample(x_in, return_softmax=True)
-            segs.append(sm)
-            errs.append(-np.log(np.maximum(np.take_along_axis(sm, s[..., None], axis=-1)[..., 0], 1e-38)))
-        segm_arr = np.squeeze(np.asarray(segs))
-        vars_ = np.mean(np.std(segm_arr, axis=0), axis=-1)
-        means = np.argmax(np.mean(segm_arr, 0), axis=-1)
-        return means, vars_, np.mean(np.squeeze(np.asarray(errs)), axis=0)
+        """phiseg_model.py:449-475: argmax of the mean softmax, class-mean of the per-class standard deviation, mean cross
+        entropy - each [H,W] for the single image the reference squeezes to."""
+        m = self._sample_maps(x_in, num_samples, s_gt=s_gt, want=('mean_arg', 'std_mean', 'err'))
+        return np.squeeze(m['mean_arg']), np.squeeze(m['std_mean']), np.squeeze(m['err'])
 
     # ---------------------------------------------------------------------------------------------------
     # weights / checkpoints (phiseg_model.py:144-148,505-525,821-845)

@@ -98,6 +98,91 @@ def test_metric_kernels(lib, oracle, pkg):
         assert abs(M.ncc_from_sums(sums.cpu().numpy(), P) - ref) < 2e-5
 
 
+def test_oracle_uncertainty_maps_known_answers(oracle):
+    """hand cases for the numpy restatement of phiseg_model.py:378-475"""
+    # two samples, one pixel, two classes: logits (0, 0) and (ln 3, 0) -> softmax (.5, .5) and (.75, .25)
+    z = np.array([[[[0.0, 0.0]]], [[[np.log(3.0), 0.0]]]])
+    arg, sd, err = oracle.mean_variance_and_error_maps(z, np.array([[1]]))
+    assert arg[0, 0] == 0 and abs(sd[0, 0] - 0.125) < 1e-12            # np.std of (.5, .75) = .125 for both classes
+    assert abs(err[0, 0] - 0.5 * (np.log(2.0) + np.log(4.0))) < 1e-12   # -log .5 and -log .25
+    # covariance of (p, 1-p) is singular: determinant 0; unbiased variance of (.5, .75) is 1/32
+    assert abs(oracle.sample_variance_sm_cov_bf(z)[0, 0]) < 1e-12
+    # clipped logits of class 0: (1e-5, 1 - 1e-5) -> population variance ((1 - 2e-5) / 2)^2
+    assert abs(oracle.sample_variance_sm_cov(z)[0, 0] - ((1 - 2e-5) / 2) ** 2) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('nl,B', [(2, 1), (4, 2)])
+def test_sample_moment_kernels(lib, oracle, nl, B):
+    """phs_sample_moments / phs_sample_maps against the oracle's stacked-sample numpy (phiseg_model.py:378-475); the
+    samples arrive in two passes of different size like a sampling plan with a remainder."""
+    h = lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(11 + nl)
+    H, W, S1, S2 = 12, 10, 5, 2
+    P = H * W
+    z = torch.randn(S1 + S2, B, H, W, nl, generator=g) * 2.0
+    gt = torch.randint(0, nl, (B, H, W), generator=g).to(torch.uint8)
+    na = nl + nl * (nl + 1) // 2 + 1
+    for kind in (0, 1):
+        acc = torch.zeros(B * P * na, dtype=torch.float64, device='cuda')
+        for part in (z[:S1], z[S1:]):
+            pd = part.contiguous().cuda()
+            lib.check(h.phs_sample_moments(pd.data_ptr(), gt.cuda().data_ptr(), part.shape[0], B, P, nl, kind, 1e-5, 1 - 1e-5,
+                                           acc.data_ptr(), st))
+        arg = torch.empty(B, H, W, dtype=torch.int64, device='cuda')
+        sd, vs, det, err = (torch.empty(B, H, W, device='cuda') for _ in range(4))
+        lib.check(h.phs_sample_maps(acc.data_ptr(), B * P, nl, S1 + S2, 1, arg.data_ptr(), sd.data_ptr(), vs.data_ptr(),
+                                    det.data_ptr(), err.data_ptr(), st))
+        torch.cuda.synchronize()
+        for b in range(B):
+            zb, gb = z[:, b].numpy(), gt[b].numpy()
+            if kind == 0:
+                r_arg, r_sd, r_err = oracle.mean_variance_and_error_maps(zb, gb)
+                assert np.array_equal(arg[b].cpu().numpy(), r_arg)
+                assert np.abs(sd[b].cpu().numpy() - r_sd).max() < 2e-6
+                assert np.abs(err[b].cpu().numpy() - r_err).max() < 1e-5
+                r_det = oracle.sample_variance_sm_cov_bf(zb)
+                assert np.abs(det[b].cpu().numpy() - r_det).max() < 1e-7 + 1e-4 * np.abs(r_det).max()
+            else:
+                assert np.abs(vs[b].cpu().numpy() - oracle.sample_variance_sm_cov(zb)).max() < 2e-6
+                # softmax rows sum to one (singular covariance, det ~ 0 above); the clipped logits give a regular matrix
+                zc = np.clip(zb.astype(np.float64), 1e-5, 1 - 1e-5).transpose((1, 2, 3, 0))
+                r_det = np.array([[np.linalg.det(np.cov(zc[i, j])) for j in range(W)] for i in range(H)])
+                assert np.abs(det[b].cpu().numpy() - r_det).max() < 1e-9 + 1e-4 * np.abs(r_det).max()
+
+
+@pytest.mark.gpu
+def test_uncertainty_maps_end_to_end(pkg, oracle):
+    """The four map methods of the class (phiseg_model.py:378-475) on device moments == the oracle's numpy on the SAME
+    samples (generate_samples with the same generator seed draws the same noise through the same sampling plan)."""
+    pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
+    ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
+    D = importlib.import_module('phiseg_code_b200.data')
+    exp = ex.load_experiment(ex.experiment_path('phiseg_7_5'))
+    exp.image_size = (64, 64, 1)
+    model = pm.phiseg(exp, mode='fast', use_cuda_graph=False)
+    model.sample_rows = 4                      # 6 samples = one pass of 4 + a remainder pass of 2
+    x, s = D.synthetic_batch(1, 64, 64, 2, seed=3)
+    S = 6
+
+    def seeded(fn):
+        model._gen.manual_seed(77)
+        return fn()
+    smp = seeded(lambda: model.generate_samples(x, S))[:, 0]                     # [S,H,W,nl] summed-level logits
+    arg, sd, err = seeded(lambda: model.predict_mean_variance_and_error_maps(s, x, S))
+    r_arg, r_sd, r_err = oracle.mean_variance_and_error_maps(smp, s[0])
+    assert arg.shape == (64, 64) and np.mean(arg == r_arg) > 0.999              # ties of the mean softmax may flip
+    assert np.abs(sd - r_sd).max() < 1e-5 and np.abs(err - r_err).max() < 1e-4 * max(1.0, r_err.max())
+    e2 = seeded(lambda: model.get_crossentropy_error_map(s, x, S))
+    assert e2.shape == (1, 64, 64) and np.array_equal(e2[0], err)
+    var = seeded(lambda: model.predict_segmentation_sample_variance_sm_cov(x, S))
+    assert np.abs(var - oracle.sample_variance_sm_cov(smp)).max() < 1e-5
+    det = seeded(lambda: model.predict_segmentation_sample_variance_sm_cov_bf(x, S))
+    r_det = oracle.sample_variance_sm_cov_bf(smp)
+    assert np.abs(det - r_det).max() < 1e-7 + 1e-3 * np.abs(r_det).max()
+
+
 @pytest.mark.gpu
 def test_validation_metrics_end_to_end(pkg, oracle, tmp_path):
     """phiseg.validation_metrics against the oracle's metrics evaluated on the SAME samples (copied back for the check), and
