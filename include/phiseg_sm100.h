@@ -21,6 +21,7 @@ extern "C" {
 
 #define PHS_F32 0
 #define PHS_BF16 1
+#define PHS_F64 2 /* only the resident images of phs_augment_batch (the reference stores np.float = float64 in its HDF5) */
 
 #define PHS_NORM_BN_TRAIN 0 /* tfwrapper/normalisation.py:145-163, is_training=True  */
 #define PHS_NORM_BN_INFER 1 /* same, is_training=False (moving statistics)            */
@@ -222,6 +223,30 @@ int phs_sample_moments(const float* logits, const uint8_t* gt, int S, int B, int
  * eigenvalue sum of :393-402), cov_det = det(np.cov) of all classes (:423-428), err = mean cross entropy (:444-446,472). */
 int phs_sample_maps(const double* acc, int64_t total_pix, int nlabels, int count, int drop_last, int64_t* mean_arg,
                     float* std_mean, float* var_sum, float* cov_det, float* err, void* stream);
+
+/* ---- input pipeline (data/batch_provider.py:43-67,131-272; utils.py:18-37) --------------------------------------------
+ * One output image of a batch: which resident image, which annotator's mask, and the random augmentation the host drew
+ * for it in the reference's np.random order.  minv = the inverted 2x3 matrix cv2.warpAffine works with (from
+ * cv2.getRotationMatrix2D((W/2, H/2), angle, 1)); crop/px/py = side and origin of the square crop that cv2.resize
+ * stretches back to H x W (rows from py, columns from px, as batch_provider.py:219 indexes them). */
+#define PHS_AUG_ROTATE 1
+#define PHS_AUG_SCALE 2
+#define PHS_AUG_FLIPLR 4
+#define PHS_AUG_FLIPUD 8
+typedef struct phs_aug_params {
+  int32_t src;   /* index into the resident images / labels */
+  int32_t annot; /* annotator plane of the labels (_select_random_label, :124-130) */
+  int32_t flags; /* PHS_AUG_* */
+  int32_t crop, px, py;
+  double minv[6];
+} phs_aug_params;
+/* x_out[B][H][W] float32, s_out[B][H][W] uint8 from the resident data set images[N][H][W] (float32 or float64) and
+ * labels[N][H][W][annotators] uint8 (labels and s_out may both be NULL), params[B] in DEVICE memory.  Applies, per image:
+ * rotation (bilinear warpAffine, constant border 0), crop + bilinear resize, flips - label masks as one-hot planes with
+ * np.argmax (nlabels <= 4, the reference's one-hot branch) - restating OpenCV's fixed-point coordinates, coefficient
+ * types and summation order.  One launch per batch, nothing intermediate is stored. */
+int phs_augment_batch(const void* images, int image_dtype, const uint8_t* labels, int H, int W, int annotators, int nlabels,
+                      const phs_aug_params* params, int B, float* x_out, uint8_t* s_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libphiseg_sm100.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'small_conv.cu', 'conv_tc.cu', 'conv_halo.cu', 'wgrad_halo.cu', 'elementwise.cu', 'latent_loss.cu', 'metrics.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'small_conv.cu', 'conv_tc.cu', 'conv_halo.cu', 'wgrad_halo.cu', 'elementwise.cu', 'latent_loss.cu', 'metrics.cu', 'augment.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
               '--expt-relaxed-constexpr', '-Xptxas', '-v']
 

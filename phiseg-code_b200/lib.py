@@ -9,7 +9,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libphiseg_sm100.so')
 
-PHS_F32, PHS_BF16 = 0, 1
+PHS_F32, PHS_BF16, PHS_F64 = 0, 1, 2
+AUG_ROTATE, AUG_SCALE, AUG_FLIPLR, AUG_FLIPUD = 1, 2, 4, 8
 NORM_BN_TRAIN, NORM_BN_INFER, NORM_GN = 0, 1, 2
 IMPL_SIMT, IMPL_TC = 0, 1
 
@@ -17,6 +18,12 @@ IMPL_SIMT, IMPL_TC = 0, 1
 class phs_tensor(ctypes.Structure):
     _fields_ = [('ptr', c_void_p), ('N', c_int32), ('H', c_int32), ('W', c_int32), ('C', c_int32),
                 ('ld', c_int32), ('dtype', c_int32)]
+
+
+class phs_aug_params(ctypes.Structure):
+    """include/phiseg_sm100.h: one output image of phs_augment_batch (72 bytes)"""
+    _fields_ = [('src', c_int32), ('annot', c_int32), ('flags', c_int32), ('crop', c_int32), ('px', c_int32),
+                ('py', c_int32), ('minv', ctypes.c_double * 6)]
 
 
 class PhisegError(RuntimeError):
@@ -70,6 +77,7 @@ SIGNATURES = {
     'phs_pairwise_label_stats': [_P, c_int, c_int, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
     'phs_ncc_maps': [_P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _S],
     'phs_sample_moments': [_P, _P, c_int, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _S],
+    'phs_augment_batch': [_P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, _S],
     'phs_sample_maps': [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, _P, _S],
 }
 

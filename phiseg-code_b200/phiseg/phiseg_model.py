@@ -328,7 +328,8 @@ class phiseg():
 
     def training_step(self, x_b, s_b, lr=None, eps=None, defer=False):
         """One iteration of the hot loop (phiseg_model.py:186-197): feed a batch, run forward, ELBO, backward and the
-        optimizer, return loss_tot.  x_b [B,H,W,C] float32, s_b [B,H,W] uint8 (host arrays).
+        optimizer, return loss_tot.  x_b [B,H,W,C] float32, s_b [B,H,W] uint8: host arrays, or CUDA tensors of those
+        shapes / dtypes (data.BatchProvider.next_batch_device), which skip the staging below.
 
         Staging is double buffered: the batch is converted into a pinned slot and copied to a device staging slot on a
         copy stream while the previous step may still be running; the step itself starts with a device-to-device copy.
@@ -342,27 +343,36 @@ class phiseg():
         p = self._pipe(sp)
         j = p.k & 1
         p.k += 1
-        p.ev_h2d[j].synchronize()                # the slot's previous copy (two steps ago) has left host memory
-        x = np.asarray(x_b)
-        s = np.asarray(s_b)
-        if x.shape != tuple(sp.h_x.shape):
-            raise ValueError('x has shape %s, expected %s' % (x.shape, tuple(sp.h_x.shape)))
-        if s.shape != tuple(sp.h_s.shape):
-            raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
-        self._check_labels(s)
-        np.copyto(p.h_x[j].numpy(), x, casting='unsafe')
-        np.copyto(p.h_s[j].numpy(), s, casting='unsafe')
-        self.h2d_bytes = p.h_x[j].numel() * 4 + p.h_s[j].numel()
         cur = torch.cuda.current_stream()
-        with torch.cuda.stream(p.copy_stream):
-            p.copy_stream.wait_event(p.ev_free[j])
-            p.d_x[j].copy_(p.h_x[j], non_blocking=True)
-            p.d_s[j].copy_(p.h_s[j], non_blocking=True)
-            p.ev_h2d[j].record(p.copy_stream)
-        cur.wait_event(p.ev_h2d[j])
-        sp.x.buf.t.copy_(p.d_x[j], non_blocking=True)
-        sp.s.copy_(p.d_s[j], non_blocking=True)
-        p.ev_free[j].record(cur)
+        if torch.is_tensor(x_b) and x_b.is_cuda:
+            # a batch that is already on the device (data.BatchProvider.next_batch_device): no host staging at all
+            if tuple(x_b.shape) != tuple(sp.h_x.shape) or tuple(s_b.shape) != tuple(sp.h_s.shape):
+                raise ValueError('x / s have shapes %s / %s, expected %s / %s'
+                                 % (tuple(x_b.shape), tuple(s_b.shape), tuple(sp.h_x.shape), tuple(sp.h_s.shape)))
+            sp.x.buf.t.copy_(x_b.reshape(sp.x.buf.t.shape), non_blocking=True)
+            sp.s.copy_(s_b, non_blocking=True)
+            self.h2d_bytes = 0
+        else:
+            p.ev_h2d[j].synchronize()                # the slot's previous copy (two steps ago) has left host memory
+            x = np.asarray(x_b)
+            s = np.asarray(s_b)
+            if x.shape != tuple(sp.h_x.shape):
+                raise ValueError('x has shape %s, expected %s' % (x.shape, tuple(sp.h_x.shape)))
+            if s.shape != tuple(sp.h_s.shape):
+                raise ValueError('s has shape %s, expected %s' % (s.shape, tuple(sp.h_s.shape)))
+            self._check_labels(s)
+            np.copyto(p.h_x[j].numpy(), x, casting='unsafe')
+            np.copyto(p.h_s[j].numpy(), s, casting='unsafe')
+            self.h2d_bytes = p.h_x[j].numel() * 4 + p.h_s[j].numel()
+            with torch.cuda.stream(p.copy_stream):
+                p.copy_stream.wait_event(p.ev_free[j])
+                p.d_x[j].copy_(p.h_x[j], non_blocking=True)
+                p.d_s[j].copy_(p.h_s[j], non_blocking=True)
+                p.ev_h2d[j].record(p.copy_stream)
+            cur.wait_event(p.ev_h2d[j])
+            sp.x.buf.t.copy_(p.d_x[j], non_blocking=True)
+            sp.s.copy_(p.d_s[j], non_blocking=True)
+            p.ev_free[j].record(cur)
         self._draw_eps(sp, eps)
         self._device_step(sp, lr)
         p.h_losses[j].copy_(sp.losses, non_blocking=True)
@@ -398,7 +408,9 @@ class phiseg():
         self.best_loss = np.inf
         for step in range(self.init_step, exp.num_iter):
             lr = self._lr_for_step(step)
-            x_b, s_b = data.train.next_batch(exp.batch_size)
+            # a device-resident provider hands the batch over as CUDA tensors (no host round trip)
+            nb = getattr(data.train, 'next_batch_device', None) or data.train.next_batch
+            x_b, s_b = nb(exp.batch_size)
             # deferred: the loss that comes back belongs to the previous step, the host never waits for the device
             loss = self.training_step(x_b, s_b, lr, defer=True)
             if step % exp.tensorboard_update_frequency == 0 and loss is not None:
