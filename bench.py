@@ -259,6 +259,39 @@ def main():
                         'hierarchy + likelihood once per sample, accumulation / argmax on device' % (batch, SAMPLES),
                 'mask_sum': int(seg.sum())}
 
+    # ---- input pipeline: the device-resident batch provider alone (host draws the reference's random
+    # parameters, one launch gathers + augments the batch), and the training loop fed by it (no host round trip)
+    feed = None
+    if rank == 0 and args.mode == 'fast':
+        lid = data.SyntheticLIDC(num_train=128, num_val=4, size=size, nlabels=nlabels, annotators=4, seed=3)
+        prov = data.BatchProvider(lid.train.images.astype(np.float64), lid.train.labels, np.arange(128), add_dummy_dimension=True,
+                                  do_augmentations=True, num_labels_per_subject=4, annotator_range=range(4),
+                                  augmentation_options={'do_rotations': True, 'do_scaleaug': True, 'nlabels': nlabels})
+        np.random.seed(0)
+        for _ in range(3):
+            prov.next_batch_device(batch)
+        torch.cuda.synchronize()
+        th = time.perf_counter()
+        for _ in range(20):
+            prov.next_batch_device(batch)
+        torch.cuda.synchronize()
+        t_prov = (time.perf_counter() - th) / 20
+        for _ in range(2):
+            model.training_step(*prov.next_batch_device(batch), lr, defer=True)
+        model.flush()
+        torch.cuda.synchronize()
+        th = time.perf_counter()
+        for _ in range(args.steps):
+            model.training_step(*prov.next_batch_device(batch), lr, defer=True)
+        model.flush()
+        torch.cuda.synchronize()
+        t_loop = (time.perf_counter() - th) / args.steps
+        feed = {'provider_images_per_s': batch / t_prov, 'provider_ms_per_batch': t_prov * 1e3,
+                'training_images_per_s': batch / t_loop, 'training_ms_per_step': t_loop * 1e3,
+                'what': 'data.BatchProvider over 128 resident 4-annotator images (float64 like the reference HDF5), random '
+                        'annotator + rotation + crop-scaling per image (phiseg_7_5.py:30-34), one phs_augment_batch launch '
+                        'per batch; training_*: phiseg.training_step(defer=True) fed with next_batch_device, host wall clock'}
+
     # ---- the dominant kernel alone (largest-FLOP convolution launch of the step), CUDA events on the launching stream
     kern = None
     if rank == 0:
@@ -312,6 +345,7 @@ def main():
                 'h2d_bytes_per_step': int(model.h2d_bytes), 'd2h_bytes_per_step': int(model.d2h_bytes),
                 'ms_per_step': dt_e2e / args.steps * 1e3},
         'sampling': samp,
+        'input_pipeline': feed,
         'roofline_step': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                           'frac': achieved / peak_tf,
                           'what': 'whole training step: %.2f algorithmic conv GFLOP/image x %d images / device step time '
