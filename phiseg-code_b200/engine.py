@@ -640,10 +640,13 @@ class Builder:
                     N, HW, C = x.N, x.H * x.W, cout
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
-                    if mode == L.NORM_BN_TRAIN and dbias is None and not os.environ.get('PHS_BN_BWD3'):
-                        # batch norm: two launches.  The reduction adds into batch totals that live in the arena the
+                    if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_BN_BWD2'):
+                        # batch norm in two launches: the reduction adds into batch totals that live in the arena the
                         # program clears once, and the apply kernel derives its coefficients (and dgamma / dbeta) from
-                        # them - no memset node and no 5-us finalize launch on the backward chain of every layer
+                        # them - no memset node and no finalize launch per layer.  Bit-identical results, but measured
+                        # SLOWER inside the step (12.36-12.38 vs 12.30 ms, tools/step_ab.py): the backward pass is bound
+                        # by the SMs' total work, not by the length of a layer's chain, and N x more blocks now contend for
+                        # the same 2C atomics.  Opt-in.
                         tot = pr.stats_vec(C * 2)
                         self.emit('phs_norm_bwd_reduce_bn', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
                                   beta, int(relu), tot.data_ptr())

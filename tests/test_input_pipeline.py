@@ -146,4 +146,5 @@ def test_training_step_consumes_device_batches(pkg):
         model = pm.phiseg(exp, mode='fast', use_cuda_graph=False, seed=11)
         model._gen.manual_seed(5)
         losses.append(model.training_step(batch[0], batch[1], lr=1e-3))
-    assert np.isfinite(losses[0]) and losses[0] == losses[1], losses
+    # same inputs either way; what remains is the run-to-run spread of the step (test_fast_mode_reproducible: <= 1.8e-7)
+    assert np.isfinite(losses[0]) and abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0]), losses
