@@ -493,6 +493,8 @@ int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs
 bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
 int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
 
+constexpr int STATS_MIN_HW_DEFAULT = 0;   // pixels per image below which phs_conv2d_stats_acc does not fuse the statistics
+
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
               int accumulate, double* stats, cudaStream_t st) {
   // the gradient w.r.t. the input is the same GEMM on the dgrad filter shadow
@@ -522,7 +524,14 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   const int yes = y->dtype == PHS_F32 ? 4 : 2;
   PHS_REQUIRE(((size_t)y->ld * yes) % 16 == 0 && aligned16(y->ptr), "conv2d_tc: output not 16-byte aligned");
   if (conv_halo_eligible(x, y, ksize) && !getenv("PHS_NO_HALO")) {
-    int rc = conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, stats, st);
+    // Few-tile layers (a CTA holds one or two tiles): the fused statistics epilogue cannot hide behind the next tile's
+    // MMAs and is pure tail (16x16x192: 47 us with, 25 us without), while one pass over the few-MB output costs ~5 us:
+    // below PHS_STATS_MIN_HW pixels per image the statistics come from a separate launch (the layout is the same).
+    const char* e = getenv("PHS_STATS_MIN_HW");      // read per call: tools/step_ab.py switches it inside one process
+    const int stats_min_hw = e ? atoi(e) : STATS_MIN_HW_DEFAULT;
+    const bool split_stats = stats && stats_prezeroed && y->H * y->W < stats_min_hw;
+    int rc = conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, split_stats ? nullptr : stats, st);
+    if (rc == 0 && split_stats) return chan_stats_run(y, stats, true, false, st);
     if (rc != -3) return rc;
   }
   if (stats) {
