@@ -65,6 +65,32 @@ int phs_conv2d_stats(const phs_tensor* x, const void* w, const float* bias, cons
  * (phs_norm_act_fwd_stats reads them). */
 int phs_conv2d_stats_acc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize,
                          double* stats, void* stream);
+/* The conv -> norm -> ReLU -> conv fusion (the composite tfwrapper/layers.py:123-135 builds, followed by the next
+ * layers.conv2D): a 3x3 forward convolution whose input is the RAW output yprev of the previous convolution.  batch_norm /
+ * group_norm2D + ReLU (tfwrapper/normalisation.py:17-36,145-163, layers.py:134-135) are applied to the activation tile in
+ * shared memory between the TMA load and the tensor-core MMAs, so the normalised activation is never written to or read
+ * from HBM (phs_norm_act_fwd_stats and its two tensor passes disappear; zero padding stays exact: halo pixels outside the
+ * image are left at zero).  `pre` describes the producer layer's normalisation; the kernel derives mean / rstd from its
+ * statistics exactly like phs_norm_act_fwd_stats (same bits), writes them to pre->mean / pre->rstd [N][C] for the backward
+ * kernels (may be NULL) and updates the batch-norm moving averages (training mode).  stats: NULL, or this layer's own fused
+ * statistics with the phs_conv2d_stats_acc contract (pre-zeroed, (N + 1) * Cout * 2 doubles).  Returns -3 (nothing
+ * launched) when the layer is not eligible - ask phs_conv2d_pre_plan first. */
+typedef struct phs_norm_pre {
+  const double* stats;       /* producer's statistics, phs_conv2d_stats_acc layout ((N + 1) * C * 2); unused for BN_INFER */
+  int32_t mode;              /* PHS_NORM_BN_TRAIN | PHS_NORM_BN_INFER | PHS_NORM_GN */
+  float eps, decay;
+  float* moving_mean;        /* [C] batch norm only (updated in training mode, read in inference mode) */
+  float* moving_var;
+  float* mean;               /* [N][C] out, may be NULL */
+  float* rstd;
+  const float* gamma;        /* [C] */
+  const float* beta;
+  int32_t relu;
+} phs_norm_pre;
+int phs_conv2d_pre(const phs_tensor* yprev, const phs_norm_pre* pre, const void* w, const float* bias, const phs_tensor* y,
+                   double* stats, void* stream);
+/* Host-only: 1 if phs_conv2d_pre takes the layer (plan[12] as phs_conv_halo_plan), 0 if not. */
+int phs_conv2d_pre_plan(const phs_tensor* x, const phs_tensor* y, int with_stats, int* plan);
 /* Host-only introspection (no device work, callable without a GPU): the launch geometry the halo-tile tcgen05 kernel
  * would use for a 3x3 layer.  plan[12] = {CTAs per SM, S, halo stages, filter stages, filter resident, staging group,
  * accumulator stages, TMEM columns, dynamic shared memory bytes, grid, tiles, BK}; accumulate bit 1 = statistics buffer
@@ -98,6 +124,12 @@ int phs_norm_act_fwd(const phs_tensor* y, const float* mean, const float* rstd, 
 /* backward of the above, three launches: sums[N][C][2] = (sum g*mask, sum g*mask*xhat) ... */
 int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, int relu, double* sums, void* stream);
+/* Same, and the activation a = act(norm(y)) is re-materialised on the way (one extra tensor write): the backward half of
+ * phs_conv2d_pre - the forward pass never wrote a, the consumer's filter gradient (phs_conv2d_wgrad) reads it.  Same bits
+ * as phs_norm_act_fwd. */
+int phs_norm_bwd_reduce_remat(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, int relu, double* sums, const phs_tensor* a,
+                              void* stream);
 /* batch_norm (training) only, two launches instead of three: only the batch totals matter, so the reduction adds straight
  * into totals[C][2] (doubles, zeroed by the caller - the engine clears one arena per step, no memset on the chain) ... */
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,

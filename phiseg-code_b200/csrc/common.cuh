@@ -175,6 +175,36 @@ __device__ __forceinline__ void stv(T* p, const float* in) {
   }
 }
 
+// ---- normalisation arithmetic shared by every kernel that applies batch_norm / group_norm2D + ReLU -----------------
+// (tfwrapper/normalisation.py:17-36,145-163, tfwrapper/layers.py:134-135).  The activation a = act(gamma*(y-mean)*rstd +
+// beta) is produced in three places - the stand-alone norm_act kernels, the operand transform of the fused convolution
+// (conv_halo.cu, PRE) and the re-materialisation in norm_bwd_reduce - and all three must give the SAME bits, so the
+// roundings are spelled out (no FMA contraction left to the compiler).
+__device__ __forceinline__ void norm_moments(double s, double q, double cnt, float eps, double* m, double* var, double* r) {
+  const double mm = s / cnt;
+  double v = __dsub_rn(q / cnt, __dmul_rn(mm, mm));
+  if (v < 0) v = 0;
+  *m = mm;
+  *var = v;
+  *r = 1.0 / sqrt(__dadd_rn(v, (double)eps));
+}
+__device__ __forceinline__ void norm_scale_shift(float gamma, float beta, float mean, float rstd, float* sc, float* sh) {
+  const float s = __fmul_rn(gamma, rstd);
+  *sc = s;
+  *sh = __fsub_rn(beta, __fmul_rn(mean, s));
+}
+__device__ __forceinline__ float norm_act1(float y, float sc, float sh, int relu) {
+  const float r = fmaf(y, sc, sh);
+  return (relu && r < 0.f) ? 0.f : r;
+}
+// batch-norm moving averages (decay 0.99, Bessel-corrected variance: tf.contrib.layers.batch_norm, normalisation.py:27-34)
+__device__ __forceinline__ void bn_moving_update(float* moving_mean, float* moving_var, int c, float decay, double m,
+                                                 double var, double cnt) {
+  const double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+  moving_mean[c] = __fadd_rn(__fmul_rn(decay, moving_mean[c]), __fmul_rn(1.f - decay, (float)m));
+  moving_var[c] = __fadd_rn(__fmul_rn(decay, moving_var[c]), __fmul_rn(1.f - decay, (float)unb));
+}
+
 // widest vector (in elements) usable for a channel-slice tensor
 static inline int pick_vec(const phs_tensor* t) {
   int es = t->dtype == PHS_BF16 ? 2 : 4;

@@ -20,7 +20,11 @@
 //           following batch_norm / group_norm2D needs (tfwrapper/normalisation.py:27-34,156) from the fp32 accumulators:
 //           32-lane butterfly transpose-reduce per 16 columns, accumulated in registers while the CTA stays inside one
 //           image (CTAs own contiguous tile ranges), then one red.global.add per (channel, quantity).
+//   warps 6-7 (PRE only): operand transform.  The activation operand is the RAW output of the previous convolution; these
+//           warps apply its batch_norm / group_norm2D + ReLU (tfwrapper/layers.py:123-135) to every landed halo tile in
+//           place, between the TMA load and the MMAs, so the normalised activation never exists in HBM.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_host.cuh"
@@ -49,7 +53,37 @@ struct HaloParams {
   int stage_g;                // 0: direct register -> global stores; 32 | 64: channels per smem-staged TMA store group
   long long* trace;           // PHS_HALO_TRACE: per-role clock64 stamps of the first CTAs (tools/trace_halo.py)
   int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
+  phs_norm_pre pre;           // PRE: normalisation of the producer layer, applied to the activation operand
+  uint32_t pre_tab;           // PRE: byte offset (from the aligned dynamic shared memory base) of the (scale, shift) table
 };
+
+// mean / rstd of channel c of sample n from the statistics the producer's epilogue left behind (phs_conv2d_stats_acc
+// layout: per-sample sums [N][C][2], then the batch totals [C][2]) - the expressions of norm_act_fwd_stats_kernel
+__device__ __forceinline__ void pre_moments(const phs_norm_pre& pre, int N, int HW, int C, int n, int c, double* m,
+                                            double* var, double* r, double* cnt) {
+  if (pre.mode == PHS_NORM_GN) {
+    const int G = max(2, C / 16), cpg = C / G;
+    const double* gs = pre.stats + ((size_t)n * C + (size_t)(c / cpg) * cpg) * 2;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { s += gs[2 * i]; q += gs[2 * i + 1]; }
+    *cnt = (double)HW * cpg;
+    norm_moments(s, q, *cnt, pre.eps, m, var, r);
+  } else {
+    const double* totals = pre.stats + (size_t)N * C * 2;
+    *cnt = (double)HW * N;
+    norm_moments(totals[2 * c], totals[2 * c + 1], *cnt, pre.eps, m, var, r);
+  }
+}
+
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t* w) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4f(uint32_t addr, float* w) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0]), "=f"(w[1]), "=f"(w[2]), "=f"(w[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
 
 template <typename T>
 __device__ __forceinline__ void store16(T* dst, const float* v, bool accumulate) {
@@ -113,12 +147,17 @@ __device__ __forceinline__ float transpose_reduce16(const float* v, int lane) {
 // accumulators as the epilogue warps (warp w and warp w+4 share TMEM lane quadrant w) and do nothing but the per-channel
 // sum / sum-of-squares reduction, which costs twice the instructions of the whole store path: with both jobs on the same
 // four warps every layer with fused statistics was epilogue-bound (+11 % at 128->128, +50 % at 32->192).
-template <int BK, bool PAIR, bool SW>
+// PRE: two transform warps (warps 6-7, 256 threads) normalise + ReLU every landed halo tile in place before the MMA
+// issuer may read it (a_full -> transform -> a_ready).  In-bounds pixels only: the TMA unit zero-filled the out-of-image
+// halo, and SAME padding pads the ACTIVATION, so those rows must stay zero.  Not combined with PAIR (the peer's tile
+// arrival is signalled on the leader's barrier only) or SW.
+template <int BK, bool PAIR, bool SW, bool PRE>
 __global__ void __launch_bounds__(SW ? 320 : 256, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * HB_MAX_A + 2 * HB_MAX_B + 4];
+  static_assert(!PRE || (!PAIR && !SW), "operand transform: single-CTA kernel without statistics warps");
+  __shared__ __align__(8) uint64_t bars[2 * HB_MAX_A + 2 * HB_MAX_B + 4 + (PRE ? HB_MAX_A : 0)];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
 
@@ -146,6 +185,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto b_empty = [&](int s) { return bar0 + 8u * (2 * HB_MAX_A + HB_MAX_B + s); };
   auto tfull = [&](int a) { return bar0 + 8u * (2 * HB_MAX_A + 2 * HB_MAX_B + a); };
   auto tempty = [&](int a) { return bar0 + 8u * (2 * HB_MAX_A + 2 * HB_MAX_B + 2 + a); };
+  auto a_ready = [&](int s) { return bar0 + 8u * (2 * HB_MAX_A + 2 * HB_MAX_B + 4 + s); };   // PRE: tile s is transformed
 
   if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -154,6 +194,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < p.na; ++s) {
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), 1);
+      if (PRE) mbar_init(a_ready(s), 2);      // one arrival per transform warp
     }
     for (int s = 0; s < p.nb; ++s) {
       mbar_init(b_full(s), 1);
@@ -257,7 +298,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       stamp();
       const uint32_t d0 = tmem_base + acc * acc_cols;
       for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(a_full(sa), pha);
+        mbar_wait(PRE ? a_ready(sa) : a_full(sa), pha);
         tc_fence_after();
         if (kc == 0) stamp();
         const uint32_t a_base_lo = desc_lo(smem0 + sa * a_stage_bytes, 16);
@@ -293,6 +334,95 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       stamp();
       if (++acc == acc_stages) { acc = 0; aph ^= 1; }
+    }
+  } else if (PRE && warp >= 6) {
+    // ---- operand transform: a = act(gamma * (y - mean) * rstd + beta) on the landed halo tile, in place ----
+    const int tt = (int)threadIdx.x - 192;            // 0..63
+    constexpr int CPR = BK / 8;                       // 16-byte chunks (8 channels) per pixel row
+    constexpr int RPI = 64 / CPR;                     // pixel rows per pass of the 64 threads
+    constexpr int U = 4;                              // rows in flight per thread
+    const int j = tt % CPR, r0 = tt / CPR;            // this thread's (logical) chunk column and first row
+    const uint32_t tab = smem0 + p.pre_tab;           // (scale, shift) per input channel of the current sample
+    const int rows = (TILE_H + 2) * HW_;
+    const uint32_t inv_hw = ((1u << 20) + HW_ - 1) / HW_;   // row / HW_ = (row * inv_hw) >> 20 for row < 2^10 * ... (rows <= 1188)
+    const int HWpix = p.H * p.W;
+    int sa = 0, cur_n = -1;
+    uint32_t pha = 0;
+    for (int it = 0, tile = tfirst; it < iters; ++it, tile += tstep) {
+      const int n = tile / tiles_per_img;
+      const int r = tile - n * tiles_per_img;
+      const int th = r / tilesW;
+      const int h0 = th * TILE_H - 1, w0 = (r - th * tilesW) * SUB_W * S - 1;      // image coordinates of halo pixel (0, 0)
+      if (n != cur_n) {
+        // coefficients of sample n (batch norm: the same for every sample, but the owner of a sample's first tile also
+        // publishes mean / rstd of that sample for the backward kernels, and the owner of tile 0 updates the moving averages)
+        named_bar_sync(2, 64);                        // nobody still reads the previous table
+        const bool owner = r == 0;
+        for (int c = tt; c < Cin; c += 64) {
+          float mf, rf;
+          if (p.pre.mode == PHS_NORM_BN_INFER) {
+            mf = p.pre.moving_mean[c];
+            rf = rsqrtf(p.pre.moving_var[c] + p.pre.eps);
+          } else {
+            double m, var, rr, cnt;
+            pre_moments(p.pre, p.N, HWpix, Cin, n, c, &m, &var, &rr, &cnt);
+            mf = (float)m;
+            rf = (float)rr;
+            if (p.pre.mode == PHS_NORM_BN_TRAIN && p.pre.moving_mean && tile == 0)
+              bn_moving_update(p.pre.moving_mean, p.pre.moving_var, c, p.pre.decay, m, var, cnt);
+          }
+          if (owner && p.pre.mean) {
+            p.pre.mean[(size_t)n * Cin + c] = mf;
+            p.pre.rstd[(size_t)n * Cin + c] = rf;
+          }
+          float sc, sh;
+          norm_scale_shift(p.pre.gamma[c], p.pre.beta[c], mf, rf, &sc, &sh);
+          st_shared_v2f(tab + (uint32_t)c * 8u, sc, sh);
+        }
+        named_bar_sync(2, 64);
+        cur_n = n;
+      }
+      for (int kc = 0; kc < kchunks; ++kc) {
+        float cf[16];                                 // (scale, shift) of this thread's 8 channels of the chunk
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ld_shared_v4f(tab + (uint32_t)(kc * BK + j * 8) * 8u + 16u * i, cf + 4 * i);
+        mbar_wait(a_full(sa), pha);
+        const uint32_t base = smem0 + sa * a_stage_bytes;
+        for (int row = r0; row < rows; row += U * RPI) {
+          uint32_t addr[U], v[U][4];
+          bool ok[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int rw = row + u * RPI;
+            const int hr = (int)(((uint32_t)rw * inv_hw) >> 20);
+            const int wc = rw - hr * HW_;
+            ok[u] = rw < rows && (unsigned)(h0 + hr) < (unsigned)p.H && (unsigned)(w0 + wc) < (unsigned)p.W;
+            // TMA swizzle (absolute address bits, stage bases are 1024-aligned): 128-byte rows XOR the chunk index with
+            // (row & 7), 64-byte rows with ((row >> 1) & 3)
+            const uint32_t x = BK == 64 ? (uint32_t)(rw & 7) : (uint32_t)((rw >> 1) & 3);
+            addr[u] = base + (uint32_t)rw * ROW + ((((uint32_t)j) ^ x) << 4);
+            if (ok[u]) ld_shared_v4(addr[u], v[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float lo = norm_act1(__uint_as_float(v[u][i] << 16), cf[4 * i], cf[4 * i + 1], p.pre.relu);
+                const float hi = norm_act1(__uint_as_float(v[u][i] & 0xffff0000u), cf[4 * i + 2], cf[4 * i + 3], p.pre.relu);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+                o[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              st_shared_v4(addr[u], o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+        fence_proxy_async();        // the generic-proxy writes above are visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready(sa));
+        if (++sa == na) { sa = 0; pha ^= 1; }
+      }
     }
   } else if (SW && warp >= 4 && warp < 8) {
     // ---- statistics warps: per-(sample, channel) sum and sum of squares of the fp32 accumulators (+ bias) ----
@@ -582,8 +712,9 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
 }
 
 // plan_out != nullptr: only choose the geometry and report it (phs_conv_halo_plan), nothing is launched
+// pre != nullptr: x is the raw output of the previous convolution and *pre its normalisation (phs_conv2d_pre)
 static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
-                          double* stats, cudaStream_t st, int* plan_out) {
+                          double* stats, cudaStream_t st, int* plan_out, const phs_norm_pre* pre = nullptr) {
   const int accumulate = accumulate_flags & 1;
   const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
   const int BK = x->C % 64 == 0 ? 64 : 32;
@@ -609,7 +740,9 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // old rule "one CTA per SM when there is at most one tile per SM" stay selectable)
   const int ctas_per_sm = e_ctas ? atoi(e_ctas) : (getenv("PHS_HALO_1CTA") ? (total_subs <= num_sms() ? 1 : 2) : 2);
   // dynamic shared memory per CTA: 228 KB per SM, 1 KB reserved + ~1.8 KB static per CTA, 1 KB alignment slack
-  const int budget_all = ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896;
+  constexpr int PRE_TAB_BYTES = 2048;      // (scale, shift) of up to 256 input channels
+  if (pre && x->C > PRE_TAB_BYTES / 8) return -3;
+  const int budget_all = (ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896) - (pre ? PRE_TAB_BYTES : 0);
   const int max_cols = ctas_per_sm == 1 ? 512 : 256;
   const int min_tiles = ctas_per_sm * num_sms();
   // CTA pairs (cta_group::2): each CTA stages half of every filter tile.  Correct (tests/test_gpu_conv_tc.py::
@@ -629,7 +762,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   const int pair_mode = e_pair ? atoi(e_pair) : 2;
   const int pair_minc = getenv("PHS_HALO_PAIR_MINC") ? atoi(getenv("PHS_HALO_PAIR_MINC")) : 32;
   const int pair_mincin = getenv("PHS_HALO_PAIR_MINCIN") ? atoi(getenv("PHS_HALO_PAIR_MINCIN")) : 32;
-  bool pair = pair_ok && y->C >= pair_minc && x->C >= pair_mincin &&
+  bool pair = pair_ok && y->C >= pair_minc && x->C >= pair_mincin && !pre &&
               (pair_mode == 1 || (pair_mode == 2 && !stats) || (pair_mode == 3 && stats));
   const int b_bytes_full = y->C * ROW;
   int b_bytes = pair ? b_bytes_full / 2 : b_bytes_full;
@@ -703,7 +836,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // <= 64 output channels with a streamed filter: a [Cout][64] filter tile feeds only 4 short MMAs per sub-tile, so
   // doubling S (one halo stage instead of two pays for it) beats prefetching the next halo tile (measured: 64x64 64->64
   // 52 -> 40 us; 128-channel outputs: no gain)
-  if (ok && !p.b_resident && p.S == 1 && y->C <= 64 && na_pref == 2 && !e_s) {
+  if (ok && !p.b_resident && p.S == 1 && y->C <= 64 && na_pref == 2 && !e_s && !pre) {
     const HaloParams keep = p;
     na_pref = 1;
     const bool ok1 = geometry(keep.stage_g) && p.S == 2 && !p.b_resident && p.nb >= keep.nb;
@@ -722,7 +855,10 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
     const char* t = getenv("PHS_HALO_TRACE");
     p.trace = t ? (long long*)strtoull(t, nullptr, 0) : nullptr;
   }
-  const int smem = p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0) + 1024;
+  p.pre_tab = (uint32_t)(p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0));
+  if (pre) p.pre = *pre;
+  else memset(&p.pre, 0, sizeof(p.pre));
+  const int smem = (int)p.pre_tab + (pre ? PRE_TAB_BYTES : 0) + 1024;
   const int ctas = ctas_per_sm * num_sms();
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   if (pair) {
@@ -747,15 +883,24 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // 128x128 64->128 218 vs 182 us, 32->32 59 vs 52 us, step 12.77 vs 12.50 ms; ten warps at 96 registers and a second
   // pass over tensor memory cost more than the shuffles they take off the store path), so they stay opt-in
   const char* e_sw = getenv("PHS_HALO_SW");
-  const bool sw = stats != nullptr && e_sw && atoi(e_sw) == 1;
+  const bool sw = stats != nullptr && e_sw && atoi(e_sw) == 1 && !pre;
 #define PHS_HALO_LAUNCH(BKV, PAIRV, SWV)                                                                  \
   do {                                                                                                    \
     static bool attr = false;                                                                             \
-    if ((rc = allow_big_smem(conv_halo_kernel<BKV, PAIRV, SWV>, &attr))) return rc;                       \
-    if (PAIRV) phs_launch_cluster2(conv_halo_kernel<BKV, PAIRV, SWV>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
-    else phs_launch(conv_halo_kernel<BKV, PAIRV, SWV>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
+    if ((rc = allow_big_smem(conv_halo_kernel<BKV, PAIRV, SWV, false>, &attr))) return rc;                \
+    if (PAIRV) phs_launch_cluster2(conv_halo_kernel<BKV, PAIRV, SWV, false>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
+    else phs_launch(conv_halo_kernel<BKV, PAIRV, SWV, false>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
   } while (0)
-  if (BK == 64) {
+#define PHS_HALO_LAUNCH_PRE(BKV)                                                                          \
+  do {                                                                                                    \
+    static bool attr = false;                                                                             \
+    if ((rc = allow_big_smem(conv_halo_kernel<BKV, false, false, true>, &attr))) return rc;               \
+    phs_launch(conv_halo_kernel<BKV, false, false, true>, grid, 256, smem, st, tmA, tmB, tmY, p);         \
+  } while (0)
+  if (pre) {
+    if (BK == 64) PHS_HALO_LAUNCH_PRE(64);
+    else PHS_HALO_LAUNCH_PRE(32);
+  } else if (BK == 64) {
     if (pair) { if (sw) PHS_HALO_LAUNCH(64, true, true); else PHS_HALO_LAUNCH(64, true, false); }
     else { if (sw) PHS_HALO_LAUNCH(64, false, true); else PHS_HALO_LAUNCH(64, false, false); }
   } else {
@@ -763,7 +908,23 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
     else { if (sw) PHS_HALO_LAUNCH(32, false, true); else PHS_HALO_LAUNCH(32, false, false); }
   }
 #undef PHS_HALO_LAUNCH
+#undef PHS_HALO_LAUNCH_PRE
   return phs_check_launch("conv_halo_kernel");
+}
+
+// phs_conv2d_pre: conv(act(norm(yprev))) with the normalisation applied to the operand tile in shared memory
+int conv2d_halo_pre(const phs_tensor* x, const phs_norm_pre* pre, const void* w, const float* bias, const phs_tensor* y,
+                    int accumulate_flags, double* stats, cudaStream_t st) {
+  return conv_halo_impl(x, w, bias, y, accumulate_flags, stats, st, nullptr, pre);
+}
+
+extern "C" int phs_conv2d_pre_plan(const phs_tensor* x, const phs_tensor* y, int with_stats, int* plan) {
+  PHS_REQUIRE(x && y && plan, "phs_conv2d_pre_plan: null argument");
+  if (!conv_halo_eligible(x, y, 3) || x->dtype != PHS_BF16 || y->dtype != PHS_BF16) return 0;
+  static double dummy_stats;
+  static phs_norm_pre dummy_pre;
+  int rc = conv_halo_impl(x, nullptr, nullptr, y, 2, with_stats ? &dummy_stats : nullptr, nullptr, plan, &dummy_pre);
+  return rc == 0 ? 1 : (rc == -3 ? 0 : rc);
 }
 
 int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,

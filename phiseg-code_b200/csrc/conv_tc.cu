@@ -490,11 +490,39 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize);
 int chan_stats_run(const phs_tensor* y, double* stats, bool with_totals, bool zero_first, cudaStream_t st);
 int conv2d_halo(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate, double* stats,
                 cudaStream_t st);
+int conv2d_halo_pre(const phs_tensor* x, const phs_norm_pre* pre, const void* w, const float* bias, const phs_tensor* y,
+                    int accumulate_flags, double* stats, cudaStream_t st);
 bool wgrad_halo_eligible(const phs_tensor* x, const phs_tensor* dy, int ksize);
 int conv2d_wgrad_halo(const phs_tensor* x, const phs_tensor* dy, float* dw, cudaStream_t st);
 
 constexpr int STATS_MIN_HW_DEFAULT = 2048;   // pixels per image below which phs_conv2d_stats_acc does not fuse the statistics
 // (in-step A/B, profiles/step_ab_stats_split_r02.txt: 0 -> 12.27-12.30 ms, 512 -> 12.25, 2048 -> 12.20, 8192 -> 12.19)
+
+static int stats_min_hw() {
+  const char* e = getenv("PHS_STATS_MIN_HW");      // read per call: tools/step_ab.py switches it inside one process
+  return e ? atoi(e) : STATS_MIN_HW_DEFAULT;
+}
+
+// phs_conv2d_pre (include/phiseg_sm100.h): 3x3 forward convolution of act(norm(yprev)), the normalisation applied to the
+// operand tile in shared memory; stats (optional) follow the phs_conv2d_stats_acc contract, including the separate
+// statistics pass for few-tile layers
+extern "C" int phs_conv2d_pre(const phs_tensor* x, const phs_norm_pre* pre, const void* w, const float* bias,
+                              const phs_tensor* y, double* stats, void* stream) {
+  PHS_REQUIRE(x && pre && w && y && x->ptr && y->ptr, "phs_conv2d_pre: null argument");
+  PHS_REQUIRE(x->N == y->N && x->H == y->H && x->W == y->W, "phs_conv2d_pre: SAME stride-1 needs equal N,H,W");
+  PHS_REQUIRE(pre->gamma && pre->beta, "phs_conv2d_pre: gamma / beta required");
+  PHS_REQUIRE(pre->mode == PHS_NORM_BN_INFER ? (pre->moving_mean && pre->moving_var) : pre->stats != nullptr,
+              "phs_conv2d_pre: mode %d needs %s", pre->mode, pre->mode == PHS_NORM_BN_INFER ? "moving statistics" : "stats");
+  PHS_REQUIRE(pre->mode == PHS_NORM_BN_TRAIN || pre->mode == PHS_NORM_BN_INFER || pre->mode == PHS_NORM_GN,
+              "phs_conv2d_pre: unknown mode %d", pre->mode);
+  PHS_REQUIRE(!pre->mean == !pre->rstd, "phs_conv2d_pre: mean and rstd go together");
+  if (x->dtype != PHS_BF16 || y->dtype != PHS_BF16 || !conv_halo_eligible(x, y, 3)) return -3;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool split_stats = stats && y->H * y->W < stats_min_hw();
+  int rc = conv2d_halo_pre(x, pre, w, bias, y, 2, split_stats ? nullptr : stats, st);
+  if (rc == 0 && split_stats) return chan_stats_run(y, stats, true, false, st);
+  return rc;
+}
 
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
               int accumulate, double* stats, cudaStream_t st) {
@@ -528,9 +556,7 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
     // Few-tile layers (a CTA holds one or two tiles): the fused statistics epilogue cannot hide behind the next tile's
     // MMAs and is pure tail (16x16x192: 47 us with, 25 us without), while one pass over the few-MB output costs ~5 us:
     // below PHS_STATS_MIN_HW pixels per image the statistics come from a separate launch (the layout is the same).
-    const char* e = getenv("PHS_STATS_MIN_HW");      // read per call: tools/step_ab.py switches it inside one process
-    const int stats_min_hw = e ? atoi(e) : STATS_MIN_HW_DEFAULT;
-    const bool split_stats = stats && stats_prezeroed && y->H * y->W < stats_min_hw;
+    const bool split_stats = stats && stats_prezeroed && y->H * y->W < stats_min_hw();
     int rc = conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, split_stats ? nullptr : stats, st);
     if (rc == 0 && split_stats) return chan_stats_run(y, stats, true, false, st);
     if (rc != -3) return rc;

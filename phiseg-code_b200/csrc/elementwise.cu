@@ -69,12 +69,15 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
 }
 
 // sums[n][c] = (sum g*mask, sum g*mask*xhat); per_sample == 0: sums[c] = the same summed over the batch
-template <typename T, int V>
+// REMAT: also write the activation (a_out).  Same grid and the same summation order as the plain variant (the partial
+// sums, and with them every bit downstream, do not depend on which variant ran); two loads in flight instead of four keep
+// it at three blocks per SM without spills.
+template <typename T, int V, bool REMAT>
 __global__ void __launch_bounds__(RED_THREADS, 3)
     norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
-                           double* __restrict__ sums, int per_sample) {
+                           double* __restrict__ sums, int per_sample, T* __restrict__ a_out, int lda) {
   PHS_PDL_PROLOGUE();
   const int n = blockIdx.y;
   const int nvec = C / V;
@@ -86,6 +89,10 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
   extern __shared__ float sm[];
   const T* gb = g + (size_t)n * HW * ldg;
   const T* yb = y + (size_t)n * HW * ldy;
+  // a_out: the activation a = act(norm(y)) is re-materialised on the way (the forward pass of a fused conv -> norm -> ReLU
+  // -> conv pair never wrote it, conv_halo.cu PRE; the filter gradient of the consumer reads it) - same bits as
+  // norm_act_fwd would have written
+  T* ab = REMAT ? a_out + (size_t)n * HW * lda : nullptr;
   for (int cv = lane_c; cv < nvec; cv += CW) {
     float s1[V], s2[V], mu[V], rs[V], ga[V], be[V];
 #pragma unroll
@@ -98,7 +105,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
       be[i] = beta[c];
     }
     if (lane_p < PL) {
-      constexpr int U = 4;
+      constexpr int U = REMAT ? 2 : 4;
       int p = p0 + lane_p;
       for (; p + (U - 1) * PL < p1; p += U * PL) {
         float gv[U][V], yv[U][V];
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
           ldv<T, V>(yb + (size_t)(p + u * PL) * ldy + cv * V, yv[u]);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             float xh = (yv[u][i] - mu[i]) * rs[i];
@@ -117,6 +124,16 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
             s1[i] += gm;
             s2[i] += gm * xh;
           }
+          if (REMAT) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              float sc, sh;      // (recomputed per element: three flops, no registers held across the loop)
+              norm_scale_shift(ga[i], be[i], mu[i], rs[i], &sc, &sh);
+              yv[u][i] = norm_act1(yv[u][i], sc, sh, relu);
+            }
+            stv<T, V>(ab + (size_t)(p + u * PL) * lda + cv * V, yv[u]);
+          }
+        }
       }
       for (; p < p1; p += PL) {
         float gv[V], yv[V];
@@ -129,6 +146,15 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
           float gm = (relu && a <= 0.f) ? 0.f : gv[i];
           s1[i] += gm;
           s2[i] += gm * xh;
+        }
+        if (REMAT) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float sc, sh;
+            norm_scale_shift(ga[i], be[i], mu[i], rs[i], &sc, &sh);
+            yv[i] = norm_act1(yv[i], sc, sh, relu);
+          }
+          stv<T, V>(ab + (size_t)p * lda + cv * V, yv);
         }
       }
       float* d = sm + ((size_t)lane_p * C + cv * V) * 2;
@@ -160,13 +186,13 @@ static int pick_chunks(int N, int slots, int max_chunks) {
   return chunks < 1 ? 1 : chunks;
 }
 
-static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size_t* smem) {
+static void red_geometry(int N, int HW, int C, int V, dim3* grid, int* ppb, size_t* smem, int blocks_per_sm = 3) {
   int nvec = C / V;
   int CW = nvec < RED_THREADS ? nvec : RED_THREADS;
   int PL = RED_THREADS / CW;
   // aim at >= ~4 blocks per SM overall while keeping >= 64 pixels per pixel-lane where possible
   int max_chunks = (HW + PL * 8 - 1) / (PL * 8);
-  int chunks = pick_chunks(N, 148 * 3, max_chunks);     // 80 registers: three blocks per SM
+  int chunks = pick_chunks(N, 148 * blocks_per_sm, max_chunks);     // 80 registers: three blocks per SM
   *ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + *ppb - 1) / *ppb;
   *grid = dim3(chunks, N);
@@ -193,23 +219,45 @@ int phs_chan_stats(const phs_tensor* y, double* stats, void* stream) {
   return chan_stats_run(y, stats, false, true, (cudaStream_t)stream);
 }
 
-int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
-                        const float* gamma, const float* beta, int relu, double* sums, void* stream) {
-  PHS_REQUIRE(g && y && g->ptr && y->ptr && sums, "phs_norm_bwd_reduce: null argument");
-  PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C,
-              "phs_norm_bwd_reduce: g/y mismatch");
+static int norm_bwd_reduce_run(const char* fn, const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                               const float* gamma, const float* beta, int relu, double* sums, const phs_tensor* a,
+                               void* stream) {
+  PHS_REQUIRE(g && y && g->ptr && y->ptr && sums, "%s: null argument", fn);
+  PHS_REQUIRE(g->dtype == y->dtype && g->N == y->N && g->H == y->H && g->W == y->W && g->C == y->C, "%s: g/y mismatch", fn);
+  PHS_REQUIRE(!a || (a->ptr && a->dtype == y->dtype && a->N == y->N && a->H == y->H && a->W == y->W && a->C == y->C),
+              "%s: a/y mismatch", fn);
   cudaStream_t st = (cudaStream_t)stream;
   int HW = y->H * y->W;
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)y->N * y->C, st);
   int v = min_vec(pick_vec(y), pick_vec(g));
+  if (a) v = min_vec(v, pick_vec(a));
   dim3 grid; int ppb; size_t smem;
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
-  PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce: C=%d too large", y->C);
-  PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
-                                                (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
-                                                rstd, gamma, beta, relu, sums, 1))));
-  return phs_check_launch("norm_bwd_reduce");
+  PHS_REQUIRE(smem <= 48 * 1024, "%s: C=%d too large", fn, y->C);
+  if (a) {
+    PHS_DISPATCH_DTYPE(y->dtype, T,
+                       PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V, true>, grid, RED_THREADS, smem, st,
+                                                  (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
+                                                  rstd, gamma, beta, relu, sums, 1, (T*)a->ptr, a->ld))));
+  } else {
+    PHS_DISPATCH_DTYPE(y->dtype, T,
+                       PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V, false>, grid, RED_THREADS, smem, st,
+                                                  (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
+                                                  rstd, gamma, beta, relu, sums, 1, (T*)nullptr, 0))));
+  }
+  return phs_check_launch(fn);
+}
+
+int phs_norm_bwd_reduce(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, int relu, double* sums, void* stream) {
+  return norm_bwd_reduce_run("phs_norm_bwd_reduce", g, y, mean, rstd, gamma, beta, relu, sums, nullptr, stream);
+}
+
+int phs_norm_bwd_reduce_remat(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, int relu, double* sums, const phs_tensor* a,
+                              void* stream) {
+  PHS_REQUIRE(a, "phs_norm_bwd_reduce_remat: null activation output");
+  return norm_bwd_reduce_run("phs_norm_bwd_reduce_remat", g, y, mean, rstd, gamma, beta, relu, sums, a, stream);
 }
 
 int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float* mean, const float* rstd,
@@ -224,9 +272,9 @@ int phs_norm_bwd_reduce_bn(const phs_tensor* g, const phs_tensor* y, const float
   red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
   PHS_REQUIRE(smem <= 48 * 1024, "phs_norm_bwd_reduce_bn: C=%d too large", y->C);
   PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V>, grid, RED_THREADS, smem, st, 
+                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V, false>, grid, RED_THREADS, smem, st, 
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
-                                                rstd, gamma, beta, relu, totals, 0))));
+                                                rstd, gamma, beta, relu, totals, 0, (T*)nullptr, 0))));
   return phs_check_launch("norm_bwd_reduce_bn");
 }
 
@@ -413,8 +461,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       int c = cv * V + k;
-      sc[k] = gamma[c] * rstd[(size_t)n * C + c];
-      sh[k] = beta[c] - mean[(size_t)n * C + c] * sc[k];
+      norm_scale_shift(gamma[c], beta[c], mean[(size_t)n * C + c], rstd[(size_t)n * C + c], &sc[k], &sh[k]);
     }
     int p = p0 + lane_p;
     for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
@@ -425,8 +472,7 @@ __global__ void __launch_bounds__(256)
       for (int u = 0; u < STREAM_U; ++u) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          float r = fmaf(v[u][k], sc[k], sh[k]);
-          v[u][k] = (relu && r < 0.f) ? 0.f : r;
+          v[u][k] = norm_act1(v[u][k], sc[k], sh[k], relu);
         }
         stv<T, V>(ab + (size_t)(p + u * PL) * lda + cv * V, v[u]);
       }
@@ -436,8 +482,7 @@ __global__ void __launch_bounds__(256)
       ldv<T, V>(yb + (size_t)p * ldy + cv * V, v);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float r = fmaf(v[k], sc[k], sh[k]);
-        v[k] = (relu && r < 0.f) ? 0.f : r;
+        v[k] = norm_act1(v[k], sc[k], sh[k], relu);
       }
       stv<T, V>(ab + (size_t)p * lda + cv * V, v);
     }
@@ -475,39 +520,27 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int c = cv * V + k;
-      double m, r;
+      double m, r, var;
       if (mode == PHS_NORM_GN) {
         const int grp = c / cpg;
         if (grp != g_cached) {
           double s = 0.0, q = 0.0;
           const double* gs = stats + ((size_t)n * C + (size_t)grp * cpg) * 2;
           for (int i = 0; i < cpg; ++i) { s += gs[2 * i]; q += gs[2 * i + 1]; }
-          const double cnt = (double)HW * cpg;
-          g_m = s / cnt;
-          double var = q / cnt - g_m * g_m;
-          if (var < 0) var = 0;
-          g_r = 1.0 / sqrt(var + (double)eps);
+          norm_moments(s, q, (double)HW * cpg, eps, &g_m, &var, &g_r);
           g_cached = grp;
         }
         m = g_m; r = g_r;
       } else {
         const double cnt = (double)HW * N;
-        m = totals[2 * c] / cnt;
-        double var = totals[2 * c + 1] / cnt - m * m;
-        if (var < 0) var = 0;
-        r = 1.0 / sqrt(var + (double)eps);
-        if (moving_mean && blockIdx.x == 0 && n == 0 && lane_p == 0) {
-          const double unb = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
-          moving_mean[c] = decay * moving_mean[c] + (1.f - decay) * (float)m;
-          moving_var[c] = decay * moving_var[c] + (1.f - decay) * (float)unb;
-        }
+        norm_moments(totals[2 * c], totals[2 * c + 1], cnt, eps, &m, &var, &r);
+        if (moving_mean && blockIdx.x == 0 && n == 0 && lane_p == 0) bn_moving_update(moving_mean, moving_var, c, decay, m, var, cnt);
       }
       if (blockIdx.x == 0 && lane_p == 0) {
         mean_out[(size_t)n * C + c] = (float)m;
         rstd_out[(size_t)n * C + c] = (float)r;
       }
-      sc[k] = gamma[c] * (float)r;
-      sh[k] = beta[c] - (float)m * sc[k];
+      norm_scale_shift(gamma[c], beta[c], (float)m, (float)r, &sc[k], &sh[k]);
     }
     int p = p0 + lane_p;
     for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
@@ -518,8 +551,7 @@ __global__ void __launch_bounds__(256)
       for (int u = 0; u < STREAM_U; ++u) {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          float r = fmaf(v[u][k], sc[k], sh[k]);
-          v[u][k] = (relu && r < 0.f) ? 0.f : r;
+          v[u][k] = norm_act1(v[u][k], sc[k], sh[k], relu);
         }
         stv<T, V>(ab + (size_t)(p + u * PL) * lda + cv * V, v[u]);
       }
@@ -529,8 +561,7 @@ __global__ void __launch_bounds__(256)
       ldv<T, V>(yb + (size_t)p * ldy + cv * V, v);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float r = fmaf(v[k], sc[k], sh[k]);
-        v[k] = (relu && r < 0.f) ? 0.f : r;
+        v[k] = norm_act1(v[k], sc[k], sh[k], relu);
       }
       stv<T, V>(ab + (size_t)p * lda + cv * V, v);
     }

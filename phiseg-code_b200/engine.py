@@ -20,6 +20,7 @@ import torch
 from . import lib as L
 
 BN_EPS, BN_DECAY, GN_EPS = 1e-3, 0.99, 1e-5   # tfwrapper/normalisation.py:145,157 and :17
+FUSE_NORM_DEFAULT = '0'     # PHS_FUSE_NORM: conv -> norm -> ReLU -> conv fusion (Builder.conv, phs_conv2d_pre)
 
 
 def num_channels(n0):
@@ -322,6 +323,8 @@ class Act:
     def __init__(self, buf, c_off, C):
         self.buf, self.c_off, self.C = buf, c_off, C
         self._desc = None
+        self.pending = None      # conv -> norm -> ReLU -> conv fusion: this activation has not been written yet (Builder.conv)
+        self.deferred = []       # ... and these emitters (the consumer's filter gradient) wait for its re-materialisation
 
     N = property(lambda s: s.buf.N)
     H = property(lambda s: s.buf.H)
@@ -495,6 +498,15 @@ class Builder:
         self.wlane = 3 if (self.use_lanes and os.environ.get('PHS_NO_WLANE') is None) else None
         self.wlanes_used = set()
         self._splits = {}       # parity_tc: (buffer, channel slice) -> its (hi, lo) bf16 pair, made once per activation
+        # conv -> norm -> ReLU -> conv fusion (phs_conv2d_pre): the consumer convolution normalises its operand tile in
+        # shared memory, the activation between the two convolutions is not written in the forward pass
+        self.fuse = cfg.mode == 'fast' and os.environ.get('PHS_FUSE_NORM', FUSE_NORM_DEFAULT) != '0'
+        self.n_fused = 0
+        # PHS_FUSE_MINCIN / PHS_FUSE_MAXHW: fuse only consumers with at least that many input channels / at most that many
+        # pixels per image (the narrow 128x128 layers are bound by the TMA load path; the transform lengthens their
+        # load -> MMA chain)
+        self.fuse_mincin = int(os.environ.get('PHS_FUSE_MINCIN', '0'))
+        self.fuse_maxhw = int(os.environ.get('PHS_FUSE_MAXHW', str(1 << 30)))
 
     # -- helpers ------------------------------------------------------------------------------------------
     def new(self, N, H, W, C, dtype=None, ld=None, zero=False):
@@ -544,7 +556,17 @@ class Builder:
         return (L.NORM_BN_TRAIN if self.training else L.NORM_BN_INFER), BN_EPS
 
     # -- layers.conv2D (tfwrapper/layers.py:94-145) ----------------------------------------------------------
-    def conv(self, x, scope, k, cout, normed=True, relu=True, out=None, need_dx=True, out_dtype=None):
+    def realize(self, x):
+        """Write a deferred activation now (its consumer turned out not to be a fusable convolution)."""
+        if x.pending is not None:
+            emit_norm = x.pending['emit']
+            x.pending = None
+            emit_norm()
+        return x
+
+    def conv(self, x, scope, k, cout, normed=True, relu=True, out=None, need_dx=True, out_dtype=None, fuse_next=False):
+        """fuse_next: the caller promises that the result feeds exactly ONE operation, issued next on the same lane; if that
+        operation is a 3x3 tensor-core convolution the normalisation + ReLU of this layer move into its operand path."""
         P, cfg, pr = self.P, self.cfg, self.prog
         wname = scope + '/W'
         cin = x.C
@@ -572,6 +594,33 @@ class Builder:
             w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
             w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
         ydt = self.adt if out_dtype is None else out_dtype
+        fpre = None             # the producer's pending normalisation when this convolution applies it itself
+        if x_real.pending is not None:
+            assert not pad_in, 'a deferred activation reached an im2col layer'
+            pend = x.pending
+            ok = (self.fuse and tc and k == 3 and ydt == L.PHS_BF16 and cin >= self.fuse_mincin
+                  and x.H * x.W <= self.fuse_maxhw)
+            if ok:
+                probe_y = L.phs_tensor(0, x.N, x.H, x.W, cout, cout, L.PHS_BF16)
+                plan = (ctypes.c_int * 12)()
+                with_stats = int(normed and self._norm_mode()[0] != L.NORM_BN_INFER)
+                ok = pr.lib.phs_conv2d_pre_plan(pend['y'].desc(), ctypes.byref(probe_y), with_stats, plan) == 1
+            if ok:
+                fpre = pend
+                x.pending = None
+                self.n_fused += 1
+            else:
+                self.realize(x)
+        x_act = x               # the activation object (x is rebound below for the im2col path)
+
+        def conv_fwd(dst, stats_ptr):
+            """the forward launch of a tensor-core layer: plain, with fused statistics, or with the operand transform"""
+            if fpre is not None:
+                self.emit('phs_conv2d_pre', fpre['y'].desc(), ctypes.byref(fpre['struct']), w_f, bias, dst.desc(), stats_ptr)
+            elif stats_ptr is not None:
+                self.emit('phs_conv2d_stats_acc', x.desc(), w_f, bias, dst.desc(), k, stats_ptr)
+            else:
+                self.emit('phs_conv2d', x.desc(), w_f, bias, dst.desc(), k, 0, 0, impl)
 
         def conv3(src, w_hi, w_lo, b, dst, dgrad, acc):
             """dst (+)= conv(src, w) through the (hi, lo) split: three tensor-core launches"""
@@ -590,7 +639,7 @@ class Builder:
             if tc3:
                 conv3(xs, w_f, w_f_lo, bias, y, 0, 0)
             else:
-                self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
+                conv_fwd(y, None)
             a = y
             nb = None
         else:
@@ -602,11 +651,11 @@ class Builder:
             if fused_stats:
                 # statistics of the following norm come out of the conv epilogue (fp32 accumulators); the arena they
                 # live in is cleared by one fill at the start of the program (build_program)
-                self.emit('phs_conv2d_stats_acc', x.desc(), w_f, bias, y.desc(), k, stats.data_ptr())
+                conv_fwd(y, stats.data_ptr())
             elif tc3:
                 conv3(xs, w_f, w_f_lo, bias, y, 0, 0)
             else:
-                self.emit('phs_conv2d', x.desc(), w_f, bias, y.desc(), k, 0, 0, impl)
+                conv_fwd(y, None)
             if cfg.norm == 'batch_norm':
                 pre = scope + '/batch_norm/BatchNorm/'
                 gamma, beta = P.ptr(pre + 'gamma'), P.ptr(pre + 'beta')
@@ -619,16 +668,29 @@ class Builder:
                 mm = mv = None
             mean, rstd = pr.vec(N * C), pr.vec(N * C)
             a = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
-            if fused_stats:
-                # finalize folded into the activation kernel (mean / rstd still land in their arrays for the backward)
-                self.emit('phs_norm_act_fwd_stats', y.desc(), stats.data_ptr(), mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
-                          rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+
+            def emit_norm():
+                if fused_stats:
+                    # finalize folded into the activation kernel (mean / rstd still land in their arrays for the backward)
+                    self.emit('phs_norm_act_fwd_stats', y.desc(), stats.data_ptr(), mode, eps, BN_DECAY, mm, mv,
+                              mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+                else:
+                    if mode != L.NORM_BN_INFER:
+                        self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
+                    self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
+                              rstd.data_ptr())
+                    self.emit('phs_norm_act_fwd', y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+
+            if (fuse_next and self.fuse and out is None and y.dtype == L.PHS_BF16
+                    and (fused_stats or mode == L.NORM_BN_INFER)):
+                # deferred: the next operation decides (Builder.conv fuses, everything else calls realize())
+                st = L.phs_norm_pre(stats.data_ptr() if mode != L.NORM_BN_INFER else None, mode, eps, BN_DECAY, mm, mv,
+                                    mean.data_ptr() if self.want_grad else None, rstd.data_ptr() if self.want_grad else None,
+                                    gamma, beta, int(relu))
+                pr.keep.append(st)
+                a.pending = {'y': y, 'struct': st, 'emit': emit_norm}
             else:
-                if mode != L.NORM_BN_INFER:
-                    self.emit('phs_chan_stats', y.desc(), stats.data_ptr())
-                self.emit('phs_norm_finalize', stats.data_ptr(), N, HW, C, mode, eps, BN_DECAY, mm, mv, mean.data_ptr(),
-                          rstd.data_ptr())
-                self.emit('phs_norm_act_fwd', y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta, int(relu), a.desc())
+                emit_norm()
             nb = (mode, stats, mean, rstd, gamma, beta, dgamma, dbeta)
 
         if self.want_grad:
@@ -640,7 +702,7 @@ class Builder:
                     N, HW, C = x.N, x.H * x.W, cout
                     dy = self.new(x.N, x.H, x.W, cout, y.dtype)
                     dbias = P.ptr(scope + '/b', 'g') if bias is not None else None
-                    if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_BN_BWD2'):
+                    if mode == L.NORM_BN_TRAIN and dbias is None and os.environ.get('PHS_BN_BWD2') and not a.deferred:
                         # batch norm in two launches: the reduction adds into batch totals that live in the arena the
                         # program clears once, and the apply kernel derives its coefficients (and dgamma / dbeta) from
                         # them - no memset node and no finalize launch per layer.  Bit-identical results, but measured
@@ -654,8 +716,20 @@ class Builder:
                                   beta, int(relu), tot.data_ptr(), dy.desc(), dgamma, dbeta, 1)
                     else:
                         sums, coef = pr.dvec(N * C * 2), pr.vec(N * C * 2)
-                        self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
-                                  beta, int(relu), sums.data_ptr())
+                        if a.deferred or (os.environ.get('PHS_REMAT_ALWAYS') and cfg.mode == 'fast' and out is None
+                                          and y.dtype == L.PHS_BF16):
+                            # the forward pass never wrote a (its consumer normalised y on the fly): the reduction pass
+                            # reads y anyway and writes a for the consumer's filter gradient, which is emitted now
+                            # (PHS_REMAT_ALWAYS: test switch - the unfused program runs the same kernel variant, so that a
+                            # fused / unfused comparison under batch norm is not blurred by the variants' last-bit differences)
+                            self.emit('phs_norm_bwd_reduce_remat', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(),
+                                      gamma, beta, int(relu), sums.data_ptr(), a.desc())
+                            for fn in a.deferred:
+                                fn()
+                            a.deferred = []
+                        else:
+                            self.emit('phs_norm_bwd_reduce', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma,
+                                      beta, int(relu), sums.data_ptr())
                         self.emit('phs_norm_bwd_finalize', sums.data_ptr(), stats.data_ptr(), mean.data_ptr(),
                                   rstd.data_ptr(), gamma, N, HW, C, mode, coef.data_ptr(), dgamma, dbeta, dbias, 1)
                         self.emit('phs_norm_bwd_apply', ga.desc(), y.desc(), mean.data_ptr(), rstd.data_ptr(), gamma, beta,
@@ -664,33 +738,35 @@ class Builder:
                 else:
                     dy = ga
                     db = P.ptr(scope + '/b', 'g') if bias is not None else None
-                lane = self.lane
-                if self.wlane is not None:
-                    # one filter-gradient lane per origin lane: the two encoders' gradients do not queue behind each other
-                    wl = self.wlane + (lane if (lane in (1, 2) and os.environ.get('PHS_WLANES', '3') != '1') else 0)
-                    pr.emit_after(lane, wl)
-                    self.lane = wl
-                    self.wlanes_used.add(wl)
-                dys = None
-                if tc3:
-                    # dy splits on the chain lane (both the filter and the input gradient read them)
-                    self.lane = lane
-                    dys = self.split(dy, cache=False)
+                dys = self.split(dy, cache=False) if tc3 else None   # on the chain lane: filter and input gradient read them
+
+                def emit_wgrad():
+                    lane = self.lane
                     if self.wlane is not None:
+                        # one filter-gradient lane per origin lane: the two encoders' gradients do not queue behind each other
+                        wl = self.wlane + (lane if (lane in (1, 2) and os.environ.get('PHS_WLANES', '3') != '1') else 0)
                         pr.emit_after(lane, wl)
                         self.lane = wl
-                if pad_in:
-                    scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
-                    self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
-                    self.emit('phs_axpy_f32', P.ptr(wname, 'g'), scratch.data_ptr(), 9 * cin_real * cout, 1.0)
-                elif tc3:
-                    dW = P.ptr(wname, 'g')
-                    self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[0].desc(), dW, db, k, 1, L.IMPL_TC)
-                    self.emit('phs_conv2d_wgrad', xs[1].desc(), dys[0].desc(), dW, None, k, 1, L.IMPL_TC)
-                    self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[1].desc(), dW, db, k, 1, L.IMPL_TC)
+                        self.wlanes_used.add(wl)
+                    if pad_in:
+                        scratch = pr.vec(cin * cout)      # [kp][cout]: the first 9*cin_real rows are dW in HWIO order
+                        self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), scratch.data_ptr(), db, 1, 0, impl)
+                        self.emit('phs_axpy_f32', P.ptr(wname, 'g'), scratch.data_ptr(), 9 * cin_real * cout, 1.0)
+                    elif tc3:
+                        dW = P.ptr(wname, 'g')
+                        self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[0].desc(), dW, db, k, 1, L.IMPL_TC)
+                        self.emit('phs_conv2d_wgrad', xs[1].desc(), dys[0].desc(), dW, None, k, 1, L.IMPL_TC)
+                        self.emit('phs_conv2d_wgrad', xs[0].desc(), dys[1].desc(), dW, db, k, 1, L.IMPL_TC)
+                    else:
+                        self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
+                    self.lane = lane
+
+                if fpre is not None:
+                    # the input activation does not exist yet: the producer's adjoint re-materialises it (it comes next on
+                    # the tape) and emits this filter gradient right behind
+                    x_act.deferred.append(emit_wgrad)
                 else:
-                    self.emit('phs_conv2d_wgrad', x.desc(), dy.desc(), P.ptr(wname, 'g'), db, k, 1, impl)
-                self.lane = lane
+                    emit_wgrad()
                 if need_dx:
                     gx = x.grad()
                     acc = int(x.grad_written())
@@ -704,6 +780,7 @@ class Builder:
 
     # -- layers.averagepool2D (tfwrapper/layers.py:44-54) ---------------------------------------------------
     def pool(self, x, out=None):
+        self.realize(x)
         y = out if out is not None else self.new(x.N, x.H // 2, x.W // 2, x.C, x.dtype)
         self.emit('phs_avgpool2_fwd', x.desc(), y.desc())
         if self.want_grad:
@@ -716,6 +793,7 @@ class Builder:
 
     # -- layers.bilinear_upsample2D (tfwrapper/layers.py:336-345) -------------------------------------------
     def up(self, x, out=None, need_dx=True):
+        self.realize(x)
         y = out if out is not None else self.new(x.N, x.H * 2, x.W * 2, x.C, x.dtype)
         self.emit('phs_upsample2_fwd', x.desc(), y.desc())
         if self.want_grad and need_dx:
@@ -729,6 +807,7 @@ class Builder:
     # -- identity with its own gradient buffer: lets a consumer on another lane write "its" dz without racing the
     #    other consumers of x; the adjoint folds the copy's gradient back into x's
     def copy(self, x):
+        self.realize(x)
         y = self.new(x.N, x.H, x.W, x.C, x.dtype)
         self.emit('phs_copy_cast', x.desc(), y.desc())
         if self.want_grad:
@@ -845,8 +924,8 @@ def build_program(cfg, params, B, kind, device, rep=1):
                 for r in range(R):
                     if r > 0:
                         h = b.pool(h)
-                    h = b.conv(h, '%s/z%d_pre_1' % (net, r), 3, nc[r], need_dx=r > 0)
-                    h = b.conv(h, '%s/z%d_pre_2' % (net, r), 3, nc[r])
+                    h = b.conv(h, '%s/z%d_pre_1' % (net, r), 3, nc[r], need_dx=r > 0, fuse_next=True)
+                    h = b.conv(h, '%s/z%d_pre_2' % (net, r), 3, nc[r], fuse_next=True)
                     out = None
                     l = r - d
                     if 0 <= l < Lv - 1:
@@ -885,11 +964,11 @@ def build_program(cfg, params, B, kind, device, rep=1):
                         mu[net][l] = b.conv(src, '%s/z%d_mu' % (net, l), 3, zd, normed=False, out_dtype=f32)
                         spre[net][l] = b.conv(src, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
                     else:
-                        u = b.conv(ups[net], '%s/z%d_ups_to_%d_c_1' % (net, l + 1, l + 1), 3, zd * cfg.n0)
+                        u = b.conv(ups[net], '%s/z%d_ups_to_%d_c_1' % (net, l + 1, l + 1), 3, zd * cfg.n0, fuse_next=True)
                         cbuf = cat[(net, l)]
                         b.conv(u, '%s/z%d_ups_to_%d_c_2' % (net, l + 1, l + 1), 3, zd * cfg.n0,
                                out=cbuf.act(nc[l + d], zd * cfg.n0))
-                        zin = b.conv(cbuf.act(), '%s/z%d_input_1' % (net, l), 3, nc[l])
+                        zin = b.conv(cbuf.act(), '%s/z%d_input_1' % (net, l), 3, nc[l], fuse_next=True)
                         zin = b.conv(zin, '%s/z%d_input_2' % (net, l), 3, nc[l])
                         mu[net][l] = b.conv(zin, '%s/z%d_mu' % (net, l), 1, zd, normed=False, out_dtype=f32)
                         spre[net][l] = b.conv(zin, '%s/z%d_sigma' % (net, l), 1, zd, normed=False, out_dtype=f32)
@@ -940,7 +1019,8 @@ def build_program(cfg, params, B, kind, device, rep=1):
                     if r > 0:
                         h = b.pool(h)
                     for t in (1, 2, 3):
-                        h = b.conv(h, '%s/conv_%d_%d' % (net, r, t), 3, nc[r], need_dx=not (r == 0 and t == 1))
+                        h = b.conv(h, '%s/conv_%d_%d' % (net, r, t), 3, nc[r], need_dx=not (r == 0 and t == 1),
+                                   fuse_next=t < 3)
                 mu[net][0] = tiled(b.conv(h, '%s/pre_mu' % net, 1, zd, normed=False, out_dtype=f32))
                 spre[net][0] = tiled(b.conv(h, '%s/pre_sigma' % net, 1, zd, normed=False, out_dtype=f32))
                 sig[net][0] = b.new(B, 1, 1, zd, f32)
@@ -1044,7 +1124,7 @@ def _phiseg_tower(b, cfg, i, z_i, cat):
     [up-sample -> conv]; the last conv writes into the first half of the level's concat buffer."""
     nc, Lv, R = cfg.nc, cfg.L, cfg.R
     d = R - Lv
-    h = b.conv(z_i, 'likelihood/z%d_post_1' % i, 3, nc[i])
+    h = b.conv(z_i, 'likelihood/z%d_post_1' % i, 3, nc[i], fuse_next=True)
     h = b.conv(h, 'likelihood/z%d_post_2' % i, 3, nc[i])
     for t in range(d):
         h = b.up(h)
@@ -1067,7 +1147,7 @@ def _phiseg_merge(b, cfg, post_z, cat):
     for i in reversed(range(Lv - 1)):
         u = b.up(post_c[i + 1])
         b.conv(u, 'likelihood/post_z%d_ups_c' % (i + 1), 3, nc[i], out=cat[i].act(nc[i], nc[i]))
-        h = b.conv(cat[i].act(), 'likelihood/post_c_%d_1' % i, 3, nc[i + d])
+        h = b.conv(cat[i].act(), 'likelihood/post_c_%d_1' % i, 3, nc[i + d], fuse_next=True)
         post_c[i] = b.conv(h, 'likelihood/post_c_%d_2' % i, 3, nc[i + d])
     # the per-level heads are independent of each other (1x1 convolutions onto nlabels channels, HBM bound): levels >= 1
     # run on their own lanes next to the big level-0 head, forward and (mirrored) backward
@@ -1120,8 +1200,8 @@ def _probunet_unet(b, cfg, x, tiled=None):
     for i in range(R):
         if i > 0:
             h = b.pool(h)
-        h = b.conv(h, 'likelihood/encoder/conv_%d_1' % i, 3, nc[i], need_dx=i > 0)
-        h = b.conv(h, 'likelihood/encoder/conv_%d_2' % i, 3, nc[i])
+        h = b.conv(h, 'likelihood/encoder/conv_%d_1' % i, 3, nc[i], need_dx=i > 0, fuse_next=True)
+        h = b.conv(h, 'likelihood/encoder/conv_%d_2' % i, 3, nc[i], fuse_next=True)
         out = None
         if i < R - 1:
             # decoder stage jj = R-2-i concatenates [up(prev) | enc[i]] (crop_and_concat, layers.py:586-622)
@@ -1140,7 +1220,7 @@ def _probunet_unet(b, cfg, x, tiled=None):
             if jj == R - 2 and t == 3:
                 rc = Buf(pr, B, H, W, nc[ii] + zd, b.adt)
                 out = rc.act(0, nc[ii])
-            h = b.conv(h, 'likelihood/decoder/conv_%d_%d' % (jj, t), 3, nc[ii], out=out)
+            h = b.conv(h, 'likelihood/decoder/conv_%d_%d' % (jj, t), 3, nc[ii], out=out, fuse_next=t < 3)
     if b.B != B:
         # one copy of the U-Net features per sample drawn for the image; z is tiled in behind them (likelihoods.py:147-151)
         big = Buf(pr, b.B, H, W, rc.ld, b.adt)

@@ -26,6 +26,13 @@ class phs_aug_params(ctypes.Structure):
                 ('py', c_int32), ('minv', ctypes.c_double * 6)]
 
 
+class phs_norm_pre(ctypes.Structure):
+    """include/phiseg_sm100.h: the producer layer's normalisation handed to phs_conv2d_pre"""
+    _fields_ = [('stats', c_void_p), ('mode', c_int32), ('eps', c_float), ('decay', c_float),
+                ('moving_mean', c_void_p), ('moving_var', c_void_p), ('mean', c_void_p), ('rstd', c_void_p),
+                ('gamma', c_void_p), ('beta', c_void_p), ('relu', c_int32)]
+
+
 class PhisegError(RuntimeError):
     pass
 
@@ -39,6 +46,8 @@ SIGNATURES = {
     'phs_conv2d': [_T, _P, _P, _T, c_int, c_int, c_int, c_int, _S],
     'phs_conv2d_stats': [_T, _P, _P, _T, c_int, _P, _S],
     'phs_conv2d_stats_acc': [_T, _P, _P, _T, c_int, _P, _S],
+    'phs_conv2d_pre': [_T, POINTER(phs_norm_pre), _P, _P, _T, _P, _S],
+    'phs_conv2d_pre_plan': [_T, _T, c_int, POINTER(c_int)],
     'phs_conv_halo_plan': [_T, _T, c_int, c_int, POINTER(c_int)],
     'phs_wgrad_halo_plan': [_T, _T, POINTER(c_int)],
     'phs_conv2d_wgrad': [_T, _T, _P, _P, c_int, c_int, c_int, _S],
@@ -47,6 +56,7 @@ SIGNATURES = {
     'phs_norm_act_fwd': [_T, _P, _P, _P, _P, c_int, _T, _S],
     'phs_norm_act_fwd_stats': [_T, _P, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, c_int, _T, _S],
     'phs_norm_bwd_reduce': [_T, _T, _P, _P, _P, _P, c_int, _P, _S],
+    'phs_norm_bwd_reduce_remat': [_T, _T, _P, _P, _P, _P, c_int, _P, _T, _S],
     'phs_norm_bwd_reduce_bn': [_T, _T, _P, _P, _P, _P, c_int, _P, _S],
     'phs_norm_bwd_apply_bn': [_T, _T, _P, _P, _P, _P, c_int, _P, _T, _P, _P, c_int, _S],
     'phs_norm_bwd_finalize': [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _S],

@@ -144,7 +144,9 @@ def test_training_program_structure(E):
     names = [s[2] for s in steps]
     # one fill per arena chunk in front of everything clears all fused-statistics buffers
     assert names[0] == 'phs_fill_f32' and sp.n_fwd > 1
-    fused = [s for s in steps if s[2] == 'phs_conv2d_stats_acc']
+    # (phs_conv2d_pre = the same with the producer's normalisation applied to the operand, PHS_FUSE_NORM; stats is argument 5
+    # of both entry points)
+    fused = [s for s in steps if s[2] == 'phs_conv2d_stats_acc' or (s[2] == 'phs_conv2d_pre' and s[1][5] is not None)]
     assert len(fused) > 80 and 'phs_conv2d_stats' not in names
     fills = [s for s in steps[:4] if s[2] == 'phs_fill_f32']
     lo = min(s[1][0] for s in fills)
@@ -163,8 +165,66 @@ def test_training_program_structure(E):
     assert set(direct) <= want
     assert all(getattr(s, 'lane', 0) >= 3 for s in wg)
     # forward convolutions: one per live conv (+ none for the dead z*_ups_to_* branches)
-    fwd_convs = [s for s in steps[:sp.n_fwd] if s[2] in ('phs_conv2d', 'phs_conv2d_stats_acc')]
+    fwd_convs = [s for s in steps[:sp.n_fwd] if s[2] in ('phs_conv2d', 'phs_conv2d_stats_acc', 'phs_conv2d_pre')]
     assert len(fwd_convs) == 131
+
+
+@pytest.mark.parametrize('arch,kind,norm,size', [('phiseg', 'train', 'batch_norm', 128), ('phiseg', 'train', 'group_norm', 64),
+                                                 ('probunet', 'train', 'batch_norm', 64), ('phiseg', 'sample', 'batch_norm', 128),
+                                                 ('phiseg', 'eval', 'group_norm', 64)])
+def test_fused_norm_program(E, monkeypatch, arch, kind, norm, size):
+    """conv -> norm -> ReLU -> conv fusion (PHS_FUSE_NORM=1): a fused pair drops the stand-alone normalisation launch of
+    the producer; in training programs its adjoint re-materialises the activation (phs_norm_bwd_reduce_remat) BEFORE the
+    consumer's filter gradient reads it, and that filter gradient still exists exactly once.  Everything else about the
+    program (lanes, launch counts of the other entry points) is unchanged."""
+    monkeypatch.setenv('PHS_FUSE_NORM', '0')
+    cfg, P, sp0 = _build(E, arch, kind, size=size, norm=norm)
+    monkeypatch.setenv('PHS_FUSE_NORM', '1')
+    cfg, P, sp1 = _build(E, arch, kind, size=size, norm=norm)
+    c0 = collections.Counter(s[2] for s in sp0.prog.steps if s[0] is not None)
+    c1 = collections.Counter(s[2] for s in sp1.prog.steps if s[0] is not None)
+    nf = c1['phs_conv2d_pre']
+    assert c0['phs_conv2d_pre'] == 0 and nf >= 8
+    _check_lanes(sp1.prog.steps)
+    _check_lanes(sp1.prog.steps[:sp1.n_fwd])
+    _check_lanes(sp1.prog.steps[sp1.n_fwd:])
+    training = kind == 'train'
+    infer_bn = norm == 'batch_norm' and not training
+    gone = 'phs_norm_act_fwd' if infer_bn else 'phs_norm_act_fwd_stats'
+    assert c0[gone] - c1[gone] == nf
+    if infer_bn:
+        assert c0['phs_norm_finalize'] - c1['phs_norm_finalize'] == nf
+    assert c1['phs_norm_bwd_reduce_remat'] == (nf if training else 0)
+    assert c0['phs_norm_bwd_reduce'] == c1['phs_norm_bwd_reduce'] + c1['phs_norm_bwd_reduce_remat']
+    assert c0['phs_conv2d'] + c0['phs_conv2d_stats_acc'] == c1['phs_conv2d'] + c1['phs_conv2d_stats_acc'] + nf
+    for name in ('phs_conv2d_wgrad', 'phs_norm_bwd_apply', 'phs_norm_bwd_finalize', 'phs_avgpool2_fwd', 'phs_upsample2_fwd'):
+        assert c0[name] == c1[name], name
+    assert sp0.conv_flop_fwd == sp1.conv_flop_fwd
+    # a fused convolution reads a RAW conv output (written by an earlier forward conv), never a normalised activation
+    ptr = lambda a: a._obj.ptr
+    steps = sp1.prog.steps
+    conv_out = set()
+    norm_out = set()
+    remat_at = {}
+    for i, st in enumerate(steps):
+        fn, args, name = st
+        if name in ('phs_conv2d_stats_acc', 'phs_conv2d'):
+            conv_out.add(ptr(args[3]))
+        elif name == 'phs_conv2d_pre':
+            assert ptr(args[0]) in conv_out and ptr(args[0]) not in norm_out
+            conv_out.add(ptr(args[4]))
+        elif name in ('phs_norm_act_fwd_stats', 'phs_norm_act_fwd'):
+            norm_out.add(ptr(args[-1]))
+        elif name == 'phs_norm_bwd_reduce_remat':
+            remat_at[ptr(args[-1])] = i
+    if training:
+        # every activation that was never written in the forward pass is read by exactly one filter gradient, after its remat
+        readers = collections.Counter()
+        for i, st in enumerate(steps):
+            if st[2] == 'phs_conv2d_wgrad' and ptr(st[1][0]) in remat_at:
+                assert i > remat_at[ptr(st[1][0])]
+                readers[ptr(st[1][0])] += 1
+        assert len(readers) == nf and set(readers.values()) == {1}
 
 
 def test_algorithmic_flops_match_the_survey(E):

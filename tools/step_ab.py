@@ -19,6 +19,22 @@ for setting in sys.argv[1:] or ['-']:
         os.environ[k] = v
     exp = ex.load_experiment(ex.experiment_path(os.environ.get('AB_CONFIG', 'phiseg_7_5')))
     model = pm.phiseg(exp, mode='fast')
+    if os.environ.get('AB_KIND') == 'sample':
+        # sampling instead of training: predict(x[B], 8) -> host masks (bench.py's `sampling` entry), wall clock
+        for _ in range(3):
+            model.predict(x, num_samples=8)
+        ts = []
+        for rep in range(3):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(5):
+                m = model.predict(x, num_samples=8)
+            torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) / 5 * 1e3)
+        print('%-40s  ms/predict(x[%d], 8) %s  mask sum %d' % (setting, B, ' '.join('%.3f' % t for t in ts), int(m.sum())), flush=True)
+        for k, v in kv:
+            os.environ.pop(k, None)
+        del model
+        torch.cuda.empty_cache()
+        continue
     sp = model._program('train', B)
     model._stage_x(sp, x); model._stage_s(sp, s)
     for _ in range(4):
