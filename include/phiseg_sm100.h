@@ -89,6 +89,13 @@ typedef struct phs_norm_pre {
 } phs_norm_pre;
 int phs_conv2d_pre(const phs_tensor* yprev, const phs_norm_pre* pre, const void* w, const float* bias, const phs_tensor* y,
                    double* stats, void* stream);
+/* Inference-mode batch norm folded into the convolution (sampling / validation graphs, phiseg_model.py:61-109,537-549):
+ * a = act(gamma * (conv(x) + bias - moving_mean) * rsqrt(moving_var + eps) + beta) in ONE launch, the affine map + ReLU
+ * applied to the fp32 accumulators in the epilogue (phs_norm_finalize + phs_norm_act_fwd and the raw convolution output
+ * disappear).  post->mode must be PHS_NORM_BN_INFER; post->stats / mean / rstd are unused.  Any tensor-core shape
+ * (Cin % 32 == 0, Cout % 16 == 0, bf16 input), ksize 1 or 3. */
+int phs_conv2d_post(const phs_tensor* x, const void* w, const float* bias, const phs_norm_pre* post, const phs_tensor* a,
+                    int ksize, void* stream);
 /* Host-only: 1 if phs_conv2d_pre takes the layer (plan[12] as phs_conv_halo_plan), 0 if not. */
 int phs_conv2d_pre_plan(const phs_tensor* x, const phs_tensor* y, int with_stats, int* plan);
 /* Host-only introspection (no device work, callable without a GPU): the launch geometry the halo-tile tcgen05 kernel

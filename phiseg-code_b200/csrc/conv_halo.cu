@@ -54,7 +54,8 @@ struct HaloParams {
   long long* trace;           // PHS_HALO_TRACE: per-role clock64 stamps of the first CTAs (tools/trace_halo.py)
   int dbg;                    // profiling switches (PHS_HALO_DBG): 1 = no TMA, 2 = no MMA, 4 = no epilogue stores
   phs_norm_pre pre;           // PRE: normalisation of the producer layer, applied to the activation operand
-  uint32_t pre_tab;           // PRE: byte offset (from the aligned dynamic shared memory base) of the (scale, shift) table
+                              // POST: THIS layer's inference-mode batch norm + ReLU, applied in the epilogue
+  uint32_t pre_tab;           // PRE / POST: byte offset (from the aligned dynamic shared memory base) of the (scale, shift) table
 };
 
 // mean / rstd of channel c of sample n from the statistics the producer's epilogue left behind (phs_conv2d_stats_acc
@@ -151,12 +152,18 @@ __device__ __forceinline__ float transpose_reduce16(const float* v, int lane) {
 // issuer may read it (a_full -> transform -> a_ready).  In-bounds pixels only: the TMA unit zero-filled the out-of-image
 // halo, and SAME padding pads the ACTIVATION, so those rows must stay zero.  Not combined with PAIR (the peer's tile
 // arrival is signalled on the leader's barrier only) or SW.
-template <int BK, bool PAIR, bool SW, bool PRE>
+// POST: inference-mode batch norm (moving statistics: known before the convolution runs) + ReLU of THIS layer folded into
+// the epilogue - a = act(gamma * (conv + bias - moving_mean) * rsqrt(moving_var + eps) + beta) leaves the kernel directly,
+// the raw convolution output is never written (sampling / validation programs: phs_norm_finalize + phs_norm_act_fwd and
+// two tensor passes per layer disappear).  The affine map is applied to the fp32 accumulator, i.e. one bf16 rounding
+// fewer than the two-launch path.
+template <int BK, bool PAIR, bool SW, bool PRE, bool POST = false>
 __global__ void __launch_bounds__(SW ? 320 : 256, 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   static_assert(!PRE || (!PAIR && !SW), "operand transform: single-CTA kernel without statistics warps");
+  static_assert(!POST || (!PRE && !SW), "epilogue normalisation: inference only (no statistics, no operand transform)");
   __shared__ __align__(8) uint64_t bars[2 * HB_MAX_A + 2 * HB_MAX_B + 4 + (PRE ? HB_MAX_A : 0)];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
@@ -212,6 +219,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   PHS_PDL_PROLOGUE();     // everything above touches only shared / tensor memory and kernel parameters
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
+  if (POST) {
+    // (scale, shift) of every output channel: the expressions of norm_finalize_kernel (inference) + norm_act_fwd_kernel
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) {
+      float sc, sh;
+      norm_scale_shift(p.pre.gamma[c], p.pre.beta[c], p.pre.moving_mean[c], rsqrtf(p.pre.moving_var[c] + p.pre.eps), &sc, &sh);
+      st_shared_v2f(smem0 + p.pre_tab + (uint32_t)c * 8u, sc, sh);
+    }
+  }
   tc_fence_before();
   if (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   else __syncthreads();
@@ -591,6 +606,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[jj * 32 + i];
+              if (POST) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  float cf[4];
+                  ld_shared_v4f(smem0 + p.pre_tab + (uint32_t)(jj * 32 + i) * 8u, cf);
+                  v[i] = norm_act1(v[i], cf[0], cf[1], p.pre.relu);
+                  v[i + 1] = norm_act1(v[i + 1], cf[2], cf[3], p.pre.relu);
+                }
+              }
               const uint32_t dst = stage0 + (sg & 1) * wbuf_bytes + my_row;
               const uint32_t slot0 = ((uint32_t)(jj * 32) & (G - 1)) >> 3;
 #pragma unroll
@@ -670,6 +694,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float v[16];
   #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias_s[j * 16 + i];
+              if (POST) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  float cf[4];
+                  ld_shared_v4f(smem0 + p.pre_tab + (uint32_t)(j * 16 + i) * 8u, cf);
+                  v[i] = norm_act1(v[i], cf[0], cf[1], p.pre.relu);
+                  v[i + 1] = norm_act1(v[i + 1], cf[2], cf[3], p.pre.relu);
+                }
+              }
               if (p.dbg & 4) {
               } else if (p.y_f32) store16<float>((float*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
               else store16<bf16>((bf16*)p.y + pix * p.y_ld + j * 16, v, p.accumulate);
@@ -713,8 +746,10 @@ bool conv_halo_eligible(const phs_tensor* x, const phs_tensor* y, int ksize) {
 
 // plan_out != nullptr: only choose the geometry and report it (phs_conv_halo_plan), nothing is launched
 // pre != nullptr: x is the raw output of the previous convolution and *pre its normalisation (phs_conv2d_pre)
+// post != nullptr: *post is THIS layer's inference-mode batch norm, applied in the epilogue (phs_conv2d_post)
 static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int accumulate_flags,
-                          double* stats, cudaStream_t st, int* plan_out, const phs_norm_pre* pre = nullptr) {
+                          double* stats, cudaStream_t st, int* plan_out, const phs_norm_pre* pre = nullptr,
+                          const phs_norm_pre* post = nullptr) {
   const int accumulate = accumulate_flags & 1;
   const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
   const int BK = x->C % 64 == 0 ? 64 : 32;
@@ -742,7 +777,8 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // dynamic shared memory per CTA: 228 KB per SM, 1 KB reserved + ~1.8 KB static per CTA, 1 KB alignment slack
   constexpr int PRE_TAB_BYTES = 2048;      // (scale, shift) of up to 256 input channels
   if (pre && x->C > PRE_TAB_BYTES / 8) return -3;
-  const int budget_all = (ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896) - (pre ? PRE_TAB_BYTES : 0);
+  if (post && (pre || stats || accumulate)) return -1;
+  const int budget_all = (ctas_per_sm == 1 ? SMEM_OPTIN - 2048 : 112896) - ((pre || post) ? PRE_TAB_BYTES : 0);
   const int max_cols = ctas_per_sm == 1 ? 512 : 256;
   const int min_tiles = ctas_per_sm * num_sms();
   // CTA pairs (cta_group::2): each CTA stages half of every filter tile.  Correct (tests/test_gpu_conv_tc.py::
@@ -857,8 +893,9 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   }
   p.pre_tab = (uint32_t)(p.na * (int)p.a_stage_bytes + p.nb * b_bytes + (p.stage_g ? 2 * 128 * 2 * p.stage_g : 0));
   if (pre) p.pre = *pre;
+  else if (post) p.pre = *post;
   else memset(&p.pre, 0, sizeof(p.pre));
-  const int smem = (int)p.pre_tab + (pre ? PRE_TAB_BYTES : 0) + 1024;
+  const int smem = (int)p.pre_tab + ((pre || post) ? PRE_TAB_BYTES : 0) + 1024;
   const int ctas = ctas_per_sm * num_sms();
   int grid = p.num_tiles < ctas ? p.num_tiles : ctas;
   if (pair) {
@@ -897,7 +934,17 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
     if ((rc = allow_big_smem(conv_halo_kernel<BKV, false, false, true>, &attr))) return rc;               \
     phs_launch(conv_halo_kernel<BKV, false, false, true>, grid, 256, smem, st, tmA, tmB, tmY, p);         \
   } while (0)
-  if (pre) {
+#define PHS_HALO_LAUNCH_POST(BKV, PAIRV)                                                                  \
+  do {                                                                                                    \
+    static bool attr = false;                                                                             \
+    if ((rc = allow_big_smem(conv_halo_kernel<BKV, PAIRV, false, false, true>, &attr))) return rc;        \
+    if (PAIRV) phs_launch_cluster2(conv_halo_kernel<BKV, PAIRV, false, false, true>, grid, 192, smem, st, tmA, tmB, tmY, p); \
+    else phs_launch(conv_halo_kernel<BKV, PAIRV, false, false, true>, grid, 192, smem, st, tmA, tmB, tmY, p); \
+  } while (0)
+  if (post) {
+    if (BK == 64) { if (pair) PHS_HALO_LAUNCH_POST(64, true); else PHS_HALO_LAUNCH_POST(64, false); }
+    else { if (pair) PHS_HALO_LAUNCH_POST(32, true); else PHS_HALO_LAUNCH_POST(32, false); }
+  } else if (pre) {
     if (BK == 64) PHS_HALO_LAUNCH_PRE(64);
     else PHS_HALO_LAUNCH_PRE(32);
   } else if (BK == 64) {
@@ -909,6 +956,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   }
 #undef PHS_HALO_LAUNCH
 #undef PHS_HALO_LAUNCH_PRE
+#undef PHS_HALO_LAUNCH_POST
   return phs_check_launch("conv_halo_kernel");
 }
 
@@ -916,6 +964,12 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
 int conv2d_halo_pre(const phs_tensor* x, const phs_norm_pre* pre, const void* w, const float* bias, const phs_tensor* y,
                     int accumulate_flags, double* stats, cudaStream_t st) {
   return conv_halo_impl(x, w, bias, y, accumulate_flags, stats, st, nullptr, pre);
+}
+
+// phs_conv2d_post: act(bn_infer(conv(x))) with the normalisation folded into the epilogue
+int conv2d_halo_post(const phs_tensor* x, const void* w, const float* bias, const phs_norm_pre* post, const phs_tensor* y,
+                     cudaStream_t st) {
+  return conv_halo_impl(x, w, bias, y, 0, nullptr, st, nullptr, nullptr, post);
 }
 
 extern "C" int phs_conv2d_pre_plan(const phs_tensor* x, const phs_tensor* y, int with_stats, int* plan) {

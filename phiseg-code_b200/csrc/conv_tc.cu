@@ -21,6 +21,7 @@
 #include <mutex>
 #include <tuple>
 #include <vector>
+#include <string.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc_host.cuh"
@@ -158,16 +159,29 @@ struct ConvParams {
   int y_ld, y_f32;
   const float* bias;
   int accumulate;
+  int post_on;          // inference-mode batch norm + ReLU of this layer folded into the epilogue (phs_conv2d_post)
+  phs_norm_pre post;
 };
 
+// post16: (scale, shift) pairs of the 16 channels, or null
+__device__ __forceinline__ void post_affine16(float* v, const float* post16, int relu) {
+  if (post16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = norm_act1(v[i], post16[2 * i], post16[2 * i + 1], relu);
+  }
+}
+
 template <typename T>
-__device__ __forceinline__ void store_row16(T* dst, const uint32_t* r, const float* bias16, bool accumulate);
+__device__ __forceinline__ void store_row16(T* dst, const uint32_t* r, const float* bias16, bool accumulate,
+                                            const float* post16 = nullptr, int relu = 0);
 
 template <>
-__device__ __forceinline__ void store_row16<bf16>(bf16* dst, const uint32_t* r, const float* bias16, bool accumulate) {
+__device__ __forceinline__ void store_row16<bf16>(bf16* dst, const uint32_t* r, const float* bias16, bool accumulate,
+                                                  const float* post16, int relu) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias16 ? bias16[i] : 0.f);
+  post_affine16(v, post16, relu);
   if (accumulate) {
     float o[16];
     ldv<bf16, 8>(dst, o);
@@ -179,10 +193,12 @@ __device__ __forceinline__ void store_row16<bf16>(bf16* dst, const uint32_t* r, 
   stv<bf16, 8>(dst + 8, v + 8);
 }
 template <>
-__device__ __forceinline__ void store_row16<float>(float* dst, const uint32_t* r, const float* bias16, bool accumulate) {
+__device__ __forceinline__ void store_row16<float>(float* dst, const uint32_t* r, const float* bias16, bool accumulate,
+                                                   const float* post16, int relu) {
   float v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (bias16 ? bias16[i] : 0.f);
+  post_affine16(v, post16, relu);
   if (accumulate) {
     float o[16];
     ldv<float, 8>(dst, o);
@@ -201,6 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[256];
+  __shared__ float post_s[512];      // (scale, shift) per output channel when p.post_on (one CTA per SM: room to spare)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t A_BYTES = 128 * BK * 2;
@@ -229,6 +246,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), 512);
   PHS_PDL_PROLOGUE();
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
+  if (p.post_on) {
+    for (int c = threadIdx.x; c < p.Cout; c += blockDim.x)
+      norm_scale_shift(p.post.gamma[c], p.post.beta[c], p.post.moving_mean[c], rsqrtf(p.post.moving_var[c] + p.post.eps),
+                       &post_s[2 * c], &post_s[2 * c + 1]);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -312,10 +334,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld16(t0 + c0, r);
         tmem_ld_wait();
         if (valid) {
+          const float* post16 = p.post_on ? post_s + 2 * c0 : nullptr;
           if (p.y_f32)
-            store_row16<float>((float*)p.y + pix * p.y_ld + c0, r, p.bias ? bias_s + c0 : nullptr, p.accumulate);
+            store_row16<float>((float*)p.y + pix * p.y_ld + c0, r, p.bias ? bias_s + c0 : nullptr, p.accumulate, post16,
+                               p.post.relu);
           else
-            store_row16<bf16>((bf16*)p.y + pix * p.y_ld + c0, r, p.bias ? bias_s + c0 : nullptr, p.accumulate);
+            store_row16<bf16>((bf16*)p.y + pix * p.y_ld + c0, r, p.bias ? bias_s + c0 : nullptr, p.accumulate, post16,
+                              p.post.relu);
         }
       }
       tc_fence_before();
@@ -524,8 +549,30 @@ extern "C" int phs_conv2d_pre(const phs_tensor* x, const phs_norm_pre* pre, cons
   return rc;
 }
 
+int conv2d_halo_post(const phs_tensor* x, const void* w, const float* bias, const phs_norm_pre* post, const phs_tensor* y,
+                     cudaStream_t st);
+static int conv2d_tc_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
+                          int accumulate, double* stats, cudaStream_t st, const phs_norm_pre* post);
+
 int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
               int accumulate, double* stats, cudaStream_t st) {
+  return conv2d_tc_impl(x, w, bias, y, ksize, dgrad, accumulate, stats, st, nullptr);
+}
+
+// phs_conv2d_post (include/phiseg_sm100.h): forward convolution + inference-mode batch norm + ReLU in one launch, any
+// tensor-core shape (halo kernel or shifted-box kernel)
+extern "C" int phs_conv2d_post(const phs_tensor* x, const void* w, const float* bias, const phs_norm_pre* post,
+                               const phs_tensor* a, int ksize, void* stream) {
+  PHS_REQUIRE(x && w && post && a && x->ptr && a->ptr, "phs_conv2d_post: null argument");
+  PHS_REQUIRE(ksize == 1 || ksize == 3, "phs_conv2d_post: ksize=%d", ksize);
+  PHS_REQUIRE(x->N == a->N && x->H == a->H && x->W == a->W, "phs_conv2d_post: SAME stride-1 needs equal N,H,W");
+  PHS_REQUIRE(post->mode == PHS_NORM_BN_INFER && post->gamma && post->beta && post->moving_mean && post->moving_var,
+              "phs_conv2d_post: inference-mode batch norm with gamma / beta / moving statistics required");
+  return conv2d_tc_impl(x, w, bias, a, ksize, 0, 0, nullptr, (cudaStream_t)stream, post);
+}
+
+static int conv2d_tc_impl(const phs_tensor* x, const void* w, const float* bias, const phs_tensor* y, int ksize, int dgrad,
+                          int accumulate, double* stats, cudaStream_t st, const phs_norm_pre* post) {
   // the gradient w.r.t. the input is the same GEMM on the dgrad filter shadow
   PHS_REQUIRE(x->dtype == PHS_BF16, "conv2d_tc: input must be bf16");
   const int stats_prezeroed = accumulate & 2;   // bit 1: the caller zeroed stats (phs_conv2d_stats_acc)
@@ -544,7 +591,12 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
       ys.C = y->C - c0 < part ? y->C - c0 : part;
       const bf16* ws = (const bf16*)w + (size_t)c0 * ksize * ksize * x->C;
       PHS_REQUIRE(stats == nullptr, "conv2d_tc: fused statistics need Cout <= 256");
-      int rc = conv2d_tc(x, ws, bias ? bias + c0 : nullptr, &ys, ksize, dgrad, accumulate, nullptr, st);
+      phs_norm_pre ps;
+      if (post) {
+        ps = *post;
+        ps.gamma += c0; ps.beta += c0; ps.moving_mean += c0; ps.moving_var += c0;
+      }
+      int rc = conv2d_tc_impl(x, ws, bias ? bias + c0 : nullptr, &ys, ksize, dgrad, accumulate, nullptr, st, post ? &ps : nullptr);
       if (rc) return rc;
     }
     return 0;
@@ -557,7 +609,8 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
     // MMAs and is pure tail (16x16x192: 47 us with, 25 us without), while one pass over the few-MB output costs ~5 us:
     // below PHS_STATS_MIN_HW pixels per image the statistics come from a separate launch (the layout is the same).
     const bool split_stats = stats && stats_prezeroed && y->H * y->W < stats_min_hw();
-    int rc = conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, split_stats ? nullptr : stats, st);
+    int rc = post ? conv2d_halo_post(x, w, bias, post, y, st)
+                  : conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, split_stats ? nullptr : stats, st);
     if (rc == 0 && split_stats) return chan_stats_run(y, stats, true, false, st);
     if (rc != -3) return rc;
   }
@@ -587,6 +640,9 @@ int conv2d_tc(const phs_tensor* x, const void* w, const float* bias, const phs_t
   p.y = y->ptr; p.y_ld = y->ld; p.y_f32 = y->dtype == PHS_F32;
   p.bias = bias;
   p.accumulate = accumulate;
+  p.post_on = post != nullptr;
+  if (post) p.post = *post;
+  else memset(&p.post, 0, sizeof(p.post));
   const int smem = stages * stage_bytes + 1024;
   const int grid = b.num < num_sms() ? b.num : num_sms();
   if (BK == 64) {

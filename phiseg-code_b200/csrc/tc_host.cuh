@@ -19,9 +19,15 @@ constexpr int SMEM_OPTIN = 227 * 1024 - 2048;
 template <typename K>
 int allow_big_smem(K kernel, bool* done) {
   if (*done) return 0;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN);
+  // (a kernel with more than 2 KB of static shared memory gets what is left of the 227 KB)
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  int limit = SMEM_OPTIN;
+  if (e == cudaSuccess && 227 * 1024 - (int)fa.sharedSizeBytes < limit) limit = 227 * 1024 - (int)fa.sharedSizeBytes;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
   if (e != cudaSuccess) {
     phs_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): %s", cudaGetErrorString(e));
+    cudaGetLastError();      // (do not leave the error behind for the caller's next runtime call)
     return (int)e;
   }
   *done = true;

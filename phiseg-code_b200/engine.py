@@ -502,6 +502,9 @@ class Builder:
         # shared memory, the activation between the two convolutions is not written in the forward pass
         self.fuse = cfg.mode == 'fast' and os.environ.get('PHS_FUSE_NORM', FUSE_NORM_DEFAULT) != '0'
         self.n_fused = 0
+        # PHS_BN_FOLD=0: keep inference-mode batch norm as separate launches (A/B switch)
+        self.fold_bn = cfg.mode == 'fast' and cfg.norm == 'batch_norm' and not training and os.environ.get('PHS_BN_FOLD', '1') != '0'
+        self.n_folded = 0
         # PHS_FUSE_MINCIN / PHS_FUSE_MAXHW: fuse only consumers with at least that many input channels / at most that many
         # pixels per image (the narrow 128x128 layers are bound by the TMA load path; the transform lengthens their
         # load -> MMA chain)
@@ -594,7 +597,13 @@ class Builder:
             w_f = P.shadow_ptr(wname, False) if tc else P.ptr(wname)
             w_d = P.shadow_ptr(wname, True) if tc else P.ptr(wname)
         ydt = self.adt if out_dtype is None else out_dtype
+        # inference-mode batch norm (moving statistics: known before the convolution runs) folds into the epilogue of every
+        # tensor-core layer: one launch instead of three, the raw convolution output is never written (phs_conv2d_post)
+        fold = (normed and tc and self.fold_bn and ydt == L.PHS_BF16 and self._norm_mode()[0] == L.NORM_BN_INFER
+                and (out is None or (out.buf.ld % 8 == 0 and out.c_off % 8 == 0)))   # (tensor-core stores: 16-byte rows)
         fpre = None             # the producer's pending normalisation when this convolution applies it itself
+        if fold:
+            self.realize(x_real)
         if x_real.pending is not None:
             assert not pad_in, 'a deferred activation reached an im2col layer'
             pend = x.pending
@@ -641,6 +650,16 @@ class Builder:
             else:
                 conv_fwd(y, None)
             a = y
+            nb = None
+        elif fold:
+            mode, eps = self._norm_mode()
+            pre = scope + '/batch_norm/BatchNorm/'
+            a = out if out is not None else self.new(x.N, x.H, x.W, cout, ydt)
+            st = L.phs_norm_pre(None, mode, eps, BN_DECAY, P.ptr(pre + 'moving_mean'), P.ptr(pre + 'moving_variance'), None,
+                                None, P.ptr(pre + 'gamma'), P.ptr(pre + 'beta'), int(relu))
+            pr.keep.append(st)
+            self.emit('phs_conv2d_post', x.desc(), w_f, bias, ctypes.byref(st), a.desc(), k)
+            self.n_folded += 1
             nb = None
         else:
             y = self.new(x.N, x.H, x.W, cout, ydt)

@@ -47,6 +47,7 @@ SIGNATURES = {
     'phs_conv2d_stats': [_T, _P, _P, _T, c_int, _P, _S],
     'phs_conv2d_stats_acc': [_T, _P, _P, _T, c_int, _P, _S],
     'phs_conv2d_pre': [_T, POINTER(phs_norm_pre), _P, _P, _T, _P, _S],
+    'phs_conv2d_post': [_T, _P, _P, POINTER(phs_norm_pre), _T, c_int, _S],
     'phs_conv2d_pre_plan': [_T, _T, c_int, POINTER(c_int)],
     'phs_conv_halo_plan': [_T, _T, c_int, c_int, POINTER(c_int)],
     'phs_wgrad_halo_plan': [_T, _T, POINTER(c_int)],

@@ -177,6 +177,7 @@ def test_fused_norm_program(E, monkeypatch, arch, kind, norm, size):
     the producer; in training programs its adjoint re-materialises the activation (phs_norm_bwd_reduce_remat) BEFORE the
     consumer's filter gradient reads it, and that filter gradient still exists exactly once.  Everything else about the
     program (lanes, launch counts of the other entry points) is unchanged."""
+    monkeypatch.setenv('PHS_BN_FOLD', '0')        # (inference-mode batch norm normally folds into the PRODUCER's epilogue)
     monkeypatch.setenv('PHS_FUSE_NORM', '0')
     cfg, P, sp0 = _build(E, arch, kind, size=size, norm=norm)
     monkeypatch.setenv('PHS_FUSE_NORM', '1')
@@ -278,3 +279,30 @@ def test_latest_checkpoint_resolution(pkg, tmp_path):
     assert pm.find_floor_in_list([0, 1000, 5000], 999) == 0
     assert pm.find_floor_in_list([0, 1000, 5000], 1000) == 1000
     assert pm.find_floor_in_list([5000, 0, 1000], 7000) == 5000
+
+
+@pytest.mark.parametrize('arch,kind', [('phiseg', 'sample'), ('phiseg', 'eval'), ('probunet', 'sample'), ('phiseg', 'from_z')])
+def test_inference_batch_norm_folds_into_the_convolution(E, monkeypatch, arch, kind):
+    """Sampling / validation programs under batch norm: every tensor-core layer is ONE launch (phs_conv2d_post: convolution +
+    moving-statistics normalisation + ReLU in the epilogue) instead of conv -> phs_norm_finalize -> phs_norm_act_fwd; only
+    the layers the CUDA-core small-channel kernels take keep the separate passes.  Training programs and group norm are
+    untouched."""
+    monkeypatch.setenv('PHS_BN_FOLD', '0')
+    cfg, P, sp0 = _build(E, arch, kind, size=128)
+    monkeypatch.setenv('PHS_BN_FOLD', '1')
+    cfg, P, sp1 = _build(E, arch, kind, size=128)
+    c0 = collections.Counter(s[2] for s in sp0.prog.steps if s[0] is not None)
+    c1 = collections.Counter(s[2] for s in sp1.prog.steps if s[0] is not None)
+    nf = c1['phs_conv2d_post']
+    assert c0['phs_conv2d_post'] == 0 and nf >= 25
+    assert c0['phs_norm_act_fwd'] - c1['phs_norm_act_fwd'] == nf
+    assert c0['phs_norm_finalize'] - c1['phs_norm_finalize'] == nf
+    assert c0['phs_conv2d'] - c1['phs_conv2d'] == nf
+    assert c1['phs_norm_act_fwd'] <= 13               # the network-input and z-input layers (1 - 3 input channels)
+    assert sp1.prog.launches() == sp0.prog.launches() - 2 * nf
+    assert sp0.conv_flop_fwd == sp1.conv_flop_fwd
+    assert sp1.prog.bytes < sp0.prog.bytes                # the raw convolution outputs are not even allocated
+    _check_lanes(sp1.prog.steps)
+    for a, k, n in (('phiseg', 'train', 'batch_norm'), ('phiseg', 'sample', 'group_norm')):
+        cfg, P, sp = _build(E, a, k, norm=n)
+        assert not any(s[2] == 'phs_conv2d_post' for s in sp.prog.steps)

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Which buffers of a fast-mode training step differ between two fresh, identical runs?  Prints, per run pair, the loss,
 the gradient tensors that differ most, and the first differing program buffers with the launches that touch them.
-  python tools/diag_determinism.py [exp] [size] [B]        (PHS_NO_LANES=1 for single-stream programs)"""
+  python tools/diag_determinism.py [exp] [size] [B]        (PHS_NO_LANES=1 for single-stream programs)
+DIAG_ENV_A / DIAG_ENV_B = "K=V K=V": environment switches of the first / second run (e.g. PHS_FUSE_NORM=0 vs 1: which
+buffers of the fused program differ from the unfused one's - the two programs allocate the same buffers in the same order)."""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -16,7 +18,10 @@ size = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 
 
-def run():
+def run(env=''):
+    for kv in env.split():
+        k, v = kv.split('=', 1)
+        os.environ[k] = v
     exp = ex.load_experiment(ex.experiment_path(name))
     exp.image_size = (size, size, 1)
     model = pm.phiseg(exp, mode='fast', use_cuda_graph=False, seed=7)
@@ -29,8 +34,8 @@ def run():
     return model, sp, loss, bufs
 
 
-m1, sp1, l1, b1 = run()
-m2, sp2, l2, b2 = run()
+m1, sp1, l1, b1 = run(os.environ.get('DIAG_ENV_A', ''))
+m2, sp2, l2, b2 = run(os.environ.get('DIAG_ENV_B', ''))
 print('lanes=%s  loss %.8f vs %.8f  rel %.2e' % (os.environ.get('PHS_NO_LANES') is None, l1, l2, abs(l1 - l2) / abs(l1)))
 g1, g2 = m1.params.g, m2.params.g
 gmax = float(g1.abs().max())
@@ -71,5 +76,15 @@ for k, (t1, t2) in enumerate(zip(b1, b2)):
                 if base <= p < base + t1.numel() * t1.element_size():
                     touch += lst
             touch.sort(key=lambda v: int(v.split(':')[0]))
-            print('buf %4d %-22s %-8s maxdiff %.3e (max %.3e)  launches: %s' % (k, tuple(t1.shape), str(t1.dtype)[6:], d, float(a.abs().max()), ' '.join(touch[:6])))
+            touch2 = []
+            base2 = t2.data_ptr()
+            for i, st in enumerate(sp2.prog.steps):
+                if st[0] is None:
+                    continue
+                for a_ in st[1]:
+                    o = getattr(a_, '_obj', None)
+                    p_ = o.ptr if (o is not None and hasattr(o, 'ld')) else (a_ if isinstance(a_, int) else None)
+                    if p_ and base2 <= p_ < base2 + t2.numel() * t2.element_size():
+                        touch2.append('%d:%s@L%d' % (i, st[2], getattr(st, 'lane', 0)))
+            print('buf %4d %-22s %-8s maxdiff %.3e (max %.3e)  launches: %s  ||  B: %s' % (k, tuple(t1.shape), str(t1.dtype)[6:], d, float(a.abs().max()), ' '.join(touch[:6]), ' '.join(touch2[:6])))
 print('%d of %d buffers differ; n_fwd=%d of %d steps' % (nd, len(b1), sp1.n_fwd, len(sp1.prog.steps)))

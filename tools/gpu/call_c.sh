@@ -1,13 +1,9 @@
 #!/bin/bash
-# conv -> norm -> ReLU -> conv fusion: whole-step equivalence (all cases, with the per-tensor diagnostic), in-step A/B by layer class
 set -x
-mkdir -p gpurun_out/r2d
+mkdir -p gpurun_out/r2f
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
-timeout 100 python -m pytest tests/test_gpu_fused_norm.py -x -q -m gpu -k "remat" > gpurun_out/r2d/tests_kernel2.log 2>&1
-echo "rc_kernel=$?" >> gpurun_out/r2d/tests_kernel2.log
-tail -3 gpurun_out/r2d/tests_kernel2.log
-timeout 400 python -m pytest tests/test_gpu_fused_norm.py -q -m gpu -s -k "same_with" --tb=line > gpurun_out/r2d/tests_step.log 2>&1
-echo "rc_step=$?" >> gpurun_out/r2d/tests_step.log
-grep -v "^$" gpurun_out/r2d/tests_step.log | tail -70
-timeout 300 python tools/step_ab.py "-" "PHS_FUSE_NORM=1" "PHS_FUSE_NORM=1 PHS_FUSE_MINCIN=128" "PHS_FUSE_NORM=1 PHS_FUSE_MINCIN=64" "PHS_FUSE_NORM=1 PHS_FUSE_MAXHW=4096" "PHS_FUSE_NORM=1 PHS_FUSE_MAXHW=1024" "-" > gpurun_out/r2d/step_ab2.log 2>&1
-cat gpurun_out/r2d/step_ab2.log | tail -8
+DIAG_ENV_A="PHS_FUSE_NORM=0" DIAG_ENV_B="PHS_FUSE_NORM=1" timeout 200 python tools/diag_determinism.py phiseg_7_5 128 4 > gpurun_out/r2f/diag_fusion.log 2>&1
+cut -c1-400 gpurun_out/r2f/diag_fusion.log | tail -45
+timeout 300 python -m pytest tests/test_gpu_fused_norm.py tests/test_gpu_model.py -q -m gpu -s -k "folded or (probunet and (sampling or batched))" --tb=short > gpurun_out/r2f/tests.log 2>&1
+echo "rc=$?" >> gpurun_out/r2f/tests.log
+grep -E "passed|failed|FAILED|fast sampling|folded|Error|assert " gpurun_out/r2f/tests.log | tail -12
