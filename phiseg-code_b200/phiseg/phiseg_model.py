@@ -58,6 +58,75 @@ def net_config_from_experiment(exp, mode):
                        weight_decay=opt('weight_decay_weight'), optimizer=optimizer_kind(exp.optimizer), mode=mode)
 
 
+class _GraphHandle:
+    """Stand-in for a TensorFlow placeholder / tensor attribute of the reference model (phiseg_model.py:26-32,85-109): the
+    evaluation scripts use them as keys of feed_dict and as fetches of model.sess.run."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return '<phiseg graph handle %s>' % self.name
+
+
+class _Session:
+    """model.sess.run(fetches, feed_dict) for the de-facto attribute API of the reference (phiseg_test_quantitative.py:49-54,
+    phiseg_makegif_samples.py:96-100): inference-time fetches of ONE prior draw per call -
+    s_out_eval, s_out_eval_sm (summed level outputs / their softmax, phiseg_model.py:107-109), s_out_eval_list,
+    s_out_eval_sm_list (per level, resized to the image, :89-102), prior_z_list_gen - and, when s_inp is fed, loss_tot of
+    the evaluation graph.  All fetches of one call come from the same launch of the sampling program (same noise), like
+    one TensorFlow session run.  Training goes through training_step / train, not through the session."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def run(self, fetches, feed_dict=None):
+        m = self.model
+        single = not isinstance(fetches, (list, tuple))
+        fl = [fetches] if single else list(fetches)
+        fd = {getattr(k, 'name', k): v for k, v in (feed_dict or {}).items()}
+        if bool(fd.get('training_time', False)):
+            raise NotImplementedError('sess.run with training_pl=True: the training graph runs through training_step() / train()')
+        if 'x_input' not in fd:
+            raise KeyError('feed_dict must feed model.x_inp')
+        x = np.asarray(fd['x_input'], dtype=np.float32)
+        names = [getattr(f, 'name', f) for f in fl]
+        known = ('s_out_eval', 's_out_eval_sm', 's_out_eval_list', 's_out_eval_sm_list', 'prior_z_list_gen', 'loss_tot')
+        for n in names:
+            if n not in known:
+                raise KeyError('fetch %r is not part of the session surface (%s)' % (n, ', '.join(known)))
+        out = {}
+        if any(n != 'loss_tot' for n in names):
+            B = int(x.shape[0])
+            sp = m._program('sample', B)
+            m._stage_x(sp, x)
+            m._sample_once(sp)
+            levels = None
+            for n in set(names):
+                if n == 's_out_eval':
+                    out[n] = m._np(sp.s_out)
+                elif n == 's_out_eval_sm':
+                    out[n] = m._np(sp.s_out_sm)
+                elif n in ('s_out_eval_list', 's_out_eval_sm_list'):
+                    levels = levels if levels is not None else m._levels_full_res(sp)
+                    if n == 's_out_eval_list':
+                        out[n] = levels
+                    else:
+                        sm = []
+                        for y in levels:
+                            e = np.exp(y - y.max(axis=-1, keepdims=True))
+                            sm.append(e / e.sum(axis=-1, keepdims=True))
+                        out[n] = sm
+                elif n == 'prior_z_list_gen':
+                    out[n] = [m._np(a.tensor()).reshape(s) for a, s in zip(sp.z, m.cfg.latent_shapes(B))]
+        if 'loss_tot' in names:
+            if 's_input' not in fd:
+                raise KeyError('loss_tot needs model.s_inp in feed_dict')
+            out['loss_tot'] = m.evaluate_losses(x, np.asarray(fd['s_input']))['total_loss']
+        res = [out[n] for n in names]
+        return res[0] if single else res
+
+
 class phiseg():
 
     def __init__(self, exp_config, mode=None, device=None, use_cuda_graph=True, seed=1234, data_parallel=True):
@@ -84,6 +153,12 @@ class phiseg():
         self._hyper = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.loss_dict = {}
         self.loss_tot = None
+        # the attribute surface the reference's evaluation scripts use (phiseg_model.py:26-32,85-109)
+        self.sess = _Session(self)
+        self.x_inp, self.s_inp = _GraphHandle('x_input'), _GraphHandle('s_input')
+        self.training_pl, self.lr_pl = _GraphHandle('training_time'), _GraphHandle('learning_rate')
+        for h in ('s_out_eval', 's_out_eval_sm', 's_out_eval_list', 's_out_eval_sm_list', 'prior_z_list_gen'):
+            setattr(self, h, _GraphHandle(h))
         self.log_dir = None
         self.gpu_launches = 0
         self.world = 1

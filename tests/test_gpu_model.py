@@ -468,3 +468,31 @@ def test_weight_decay_end_to_end(pkg, oracle):
         got = model.params.view(name, model.params.g).cpu().numpy()
         want = g[name].numpy() if g[name] is not None else 1e-4 * P[name].numpy()
         assert _rel(got, want) < 5e-3, name
+
+
+def test_session_attribute_api(pkg, oracle):
+    """The de-facto attribute API of the reference's evaluation scripts (phiseg_test_quantitative.py:49-54,
+    phiseg_makegif_samples.py:96-100): model.sess.run(model.s_out_eval_sm, feed_dict={model.training_pl: False,
+    model.x_inp: x}).  All fetches of one call belong to one prior draw and equal what the method API returns for the same
+    noise."""
+    model, orc, x, s, eps = _setup(pkg, oracle, 'phiseg_7_5', 2, mode='fast', graph=True)
+    fd = {model.training_pl: False, model.x_inp: x}
+    model._gen.manual_seed(5)
+    sm, lg, lv, z = model.sess.run([model.s_out_eval_sm, model.s_out_eval, model.s_out_eval_list, model.prior_z_list_gen], feed_dict=fd)
+    model._gen.manual_seed(5)
+    ref = model.predict_segmentation_sample(x, return_softmax=True)
+    assert sm.shape == (2, SIZE, SIZE, 2) and np.array_equal(sm, ref)
+    assert len(lv) == 5 and all(a.shape == (2, SIZE, SIZE, 2) for a in lv)
+    assert np.allclose(np.sum(lv, axis=0), lg, atol=1e-4)                    # _aggregate_output_list, phiseg_model.py:210-226
+    assert len(z) == 5 and z[0].shape[0] == 2
+    # the quantitative script's pattern: one image tiled n_samples times, one fetch, not a list
+    xt = np.tile(x[:1], [6, 1, 1, 1])
+    arr = model.sess.run(model.s_out_eval_sm, feed_dict={model.training_pl: False, model.x_inp: xt})
+    assert arr.shape == (6, SIZE, SIZE, 2) and np.allclose(arr.sum(-1), 1.0, atol=1e-5)
+    assert not np.array_equal(arr[0], arr[1])                                # six different prior draws of the same image
+    tot = model.sess.run('loss_tot', feed_dict={model.training_pl: False, model.x_inp: x, model.s_inp: s})
+    assert np.isfinite(tot)
+    with pytest.raises(NotImplementedError):
+        model.sess.run(model.s_out_eval_sm, feed_dict={model.training_pl: True, model.x_inp: x})
+    with pytest.raises(KeyError):
+        model.sess.run(model.s_out_eval_sm, feed_dict={model.training_pl: False})
