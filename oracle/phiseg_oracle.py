@@ -158,7 +158,7 @@ def he_normal(rng, shape):
 # the model
 # ----------------------------------------------------------------------------
 class Oracle:
-    """Restatement of phiseg/phiseg_model.py:20-141 for the 'phiseg' and 'probunet' architectures."""
+    """Restatement of phiseg/phiseg_model.py:20-141 for the 'phiseg', 'probunet' and 'det_unet' architectures."""
 
     def __init__(self, arch='phiseg', image_size=(128, 128, 1), nlabels=2, zdim0=2, n0=32,
                  resolution_levels=7, latent_levels=5, norm='batch_norm',
@@ -221,10 +221,12 @@ class Oracle:
             for i in range(L):
                 cin = nc[i + R - L] if i < L - 1 else nc[L - 1]
                 s.conv('%s/y_lvl%d' % (net, i), 1, cin, self.nlabels, nrm, False)
-        elif self.arch == 'probunet':
+        elif self.arch in ('probunet', 'det_unet'):
             # prob_unet2D passes add_bias explicitly: False under batch_norm, True otherwise
             # (posteriors.py:25, priors.py:22, likelihoods.py:103)
-            for net, cin0 in (('posterior', self.Cx + self.nlabels), ('prior', self.Cx)):
+            # det_unet2D (likelihoods.py:10-79, with posteriors.dummy / priors.dummy): the same U-Net, no encoders, no z
+            det = self.arch == 'det_unet'
+            for net, cin0 in (() if det else (('posterior', self.Cx + self.nlabels), ('prior', self.Cx))):
                 for i in range(R):
                     for t in (1, 2, 3):
                         cin = (cin0 if i == 0 else nc[i - 1]) if t == 1 else nc[i]
@@ -243,7 +245,7 @@ class Oracle:
                 s.conv('%s/decoder/conv_%d_2' % (net, jj), 3, nc[ii], nc[ii], nrm, True)
                 s.conv('%s/decoder/conv_%d_3' % (net, jj), 3, nc[ii], nc[ii], nrm, True)
                 prev = nc[ii]
-            s.conv('%s/recomb_0' % net, 1, prev + z0, nc[0], nrm, True)
+            s.conv('%s/recomb_0' % net, 1, prev + (0 if det else z0), nc[0], nrm, True)
             s.conv('%s/recomb_1' % net, 1, nc[0], nc[0], nrm, True)
             s.conv('%s/recomb_2' % net, 1, nc[0], nc[0], nrm, True)
             s.conv('%s/prediction' % net, 1, nc[0], self.nlabels, nrm, False)
@@ -386,9 +388,10 @@ class Oracle:
             h = torch.cat([bilinear_upsample2d(h), enc[ii - 1]], dim=3)   # crop_and_concat, same sizes
             for t in (1, 2, 3):
                 h = conv(h, 'decoder/conv_%d_%d' % (jj, t))
-        z = z_list[0]
-        bz = z.reshape(z.shape[0], 1, 1, z.shape[1]).expand(-1, self.H, self.W, -1)
-        h = torch.cat([h, bz], dim=-1)
+        if self.arch != 'det_unet':                    # likelihoods.py:147-151 (det_unet2D: :69 feeds the decoder output)
+            z = z_list[0]
+            bz = z.reshape(z.shape[0], 1, 1, z.shape[1]).expand(-1, self.H, self.W, -1)
+            h = torch.cat([h, bz], dim=-1)
         for t in range(3):
             # recomb_* are 1x1 convs
             h = conv(h, 'recomb_%d' % t)
@@ -444,6 +447,13 @@ class Oracle:
         (phiseg_model.py:37-83,113-130)."""
         x = x.to(self.dtype)
         s_oh = self.one_hot(s)
+        if self.arch == 'det_unet':
+            # posteriors.dummy / priors.dummy (posteriors.py:135-138, priors.py:130-133): constants, no KL term
+            assert self.KL_weight is None, 'det_unet2D has no latent variables: KL_divergence_loss_weight must be None'
+            s_out = self.likelihood(None, x, training, new_stats)
+            ld = self.losses(s, s_out, None, None, None, None)
+            return SimpleNamespace(z=[], mu=[], sigma=[], prior_z=[], prior_mu=[], prior_sigma=[], s_out_list=s_out,
+                                   loss_dict=ld)
         if eps_prior is None:
             eps_prior = [torch.zeros_like(e) for e in eps_post]
         z, mu, sigma = self.posterior(x, s_oh, eps_post, training, new_stats)
@@ -456,7 +466,10 @@ class Oracle:
     def forward_sample(self, x, eps_prior, training=False):
         """prior(generation_mode=True) -> likelihood(prior z) -> sum over levels (phiseg_model.py:61-109)."""
         x = x.to(self.dtype)
-        pz, pmu, psigma = self.prior(None, x, eps_prior, True, training)
+        if self.arch == 'det_unet':
+            pz, pmu, psigma = [], [], []
+        else:
+            pz, pmu, psigma = self.prior(None, x, eps_prior, True, training)
         s_list = self.likelihood(pz, x, training)
         s_out = s_list[-1]
         for i in range(len(s_list) - 1):
@@ -465,6 +478,8 @@ class Oracle:
                                s_out_eval=s_out, s_out_eval_sm=torch.softmax(s_out, dim=-1))
 
     def latent_shapes(self, B):
+        if self.arch == 'det_unet':
+            return []
         if self.arch == 'probunet':
             return [(B, self.zdim0)]
         d = self.R - self.L

@@ -34,7 +34,7 @@ class NetConfig:
     def __init__(self, arch='phiseg', image_size=(128, 128, 1), nlabels=2, zdim0=2, n0=32, resolution_levels=7,
                  latent_levels=5, norm='batch_norm', KL_weight=1.0, xent_weight=1.0, exponential_weighting=True,
                  weight_decay=None, optimizer='adam', mode='parity'):
-        assert arch in ('phiseg', 'probunet'), arch
+        assert arch in ('phiseg', 'probunet', 'det_unet'), arch
         assert norm in ('batch_norm', 'group_norm'), norm
         assert mode in ('parity', 'fast', 'parity_tc'), mode
         self.arch = arch
@@ -48,13 +48,15 @@ class NetConfig:
         self.optimizer = optimizer
         self.mode = mode
         self.nc = num_channels(n0)
-        if arch == 'probunet':
+        if arch in ('probunet', 'det_unet'):
             assert latent_levels == 1
         d = 1 << (resolution_levels - 1)
         if self.H % d or self.W % d:
             raise ValueError('image size %dx%d is not divisible by 2^(resolution_levels-1)=%d' % (self.H, self.W, d))
 
     def latent_shapes(self, B):
+        if self.arch == 'det_unet':
+            return []                   # posteriors.dummy / priors.dummy: no latent variables (likelihoods.py:10-79)
         if self.arch == 'probunet':
             return [(B, self.zdim0)]
         d = self.R - self.L
@@ -121,7 +123,9 @@ def build_spec(cfg):
             conv('%s/y_lvl%d' % (net, i), 1, nc[Lv - 1] if i == Lv - 1 else nc[i + d], cfg.nlabels, False)
     else:
         # prob_unet2D passes add_bias explicitly (posteriors.py:25): off under batch_norm, on otherwise
-        for net, cin0 in (('posterior', cfg.Cx + cfg.nlabels), ('prior', cfg.Cx)):
+        # det_unet2D (likelihoods.py:10-79): the same U-Net without the encoders and without z behind the decoder
+        det = cfg.arch == 'det_unet'
+        for net, cin0 in (() if det else (('posterior', cfg.Cx + cfg.nlabels), ('prior', cfg.Cx))):
             for i in range(R):
                 for t in (1, 2, 3):
                     conv('%s/conv_%d_%d' % (net, i, t), 3, (cin0 if i == 0 else nc[i - 1]) if t == 1 else nc[i], nc[i], True)
@@ -138,7 +142,7 @@ def build_spec(cfg):
             conv('%s/decoder/conv_%d_2' % (net, jj), 3, nc[ii], nc[ii], True)
             conv('%s/decoder/conv_%d_3' % (net, jj), 3, nc[ii], nc[ii], True)
             prev = nc[ii]
-        conv('%s/recomb_0' % net, 1, prev + z0, nc[0], True)
+        conv('%s/recomb_0' % net, 1, prev + (0 if det else z0), nc[0], True)
         conv('%s/recomb_1' % net, 1, nc[0], nc[0], True)
         conv('%s/recomb_2' % net, 1, nc[0], nc[0], True)
         conv('%s/prediction' % net, 1, nc[0], cfg.nlabels, False)
@@ -918,6 +922,8 @@ def build_program(cfg, params, B, kind, device, rep=1):
         pr.emit('phs_fill_f32', sp.losses.data_ptr(), sp.losses.numel(), 0.0)
 
     nets = []
+    if cfg.arch == 'det_unet':
+        need_post = need_prior = False      # posteriors.dummy / priors.dummy
     if need_post:
         pin = b.new(Bi, H, W, Cx + nl)
         pr.emit('phs_posterior_input', sp.x.ptr, sp.s.data_ptr(), Bi, H, W, Cx, nl, pin.desc())
@@ -1015,6 +1021,17 @@ def build_program(cfg, params, B, kind, device, rep=1):
             sp.z = [b.new(*shapes[l], f32) for l in range(Lv)]          # fed by the caller ('from_z')
         if need_lik and not (nets and b.use_lanes):
             sp.logits = _phiseg_likelihood(b, cfg, sp.z)
+    elif cfg.arch == 'det_unet':
+        # likelihoods.det_unet2D: U-Net -> three 1x1 recombination convs -> prediction; nothing is sampled
+        sp.z = []
+        if need_lik:
+            rc, hC = _probunet_unet(b, cfg, sp.x, tiled, zd=0)
+            h = rc.act(0, hC)
+            for t in range(3):
+                h = b.conv(h, 'likelihood/recomb_%d' % t, 1, cfg.nc[0])
+            sp.logits = [b.conv(h, 'likelihood/prediction', 1, cfg.nlabels, normed=False, out_dtype=L.PHS_F32)]
+            if kind == 'sample':
+                sp.n_enc = len(pr.steps)     # everything depends on x alone: only the aggregation is replayed per "draw"
     else:
         if nets:
             mu = {n: [None] for n, _ in nets}
@@ -1207,10 +1224,11 @@ def _probunet_likelihood(b, cfg, z, x):
     return _probunet_head(b, cfg, z, rc, hC)
 
 
-def _probunet_unet(b, cfg, x, tiled=None):
+def _probunet_unet(b, cfg, x, tiled=None, zd=None):
     """The U-Net of likelihoods.prob_unet2D up to the point where z is tiled in (likelihoods.py:104-146): it does not
     depend on z, so it can run on its own lane next to the posterior / prior encoders."""
-    nc, R, zd = cfg.nc, cfg.R, cfg.zdim0
+    nc, R = cfg.nc, cfg.R
+    zd = cfg.zdim0 if zd is None else zd  # channels reserved behind the decoder output for the broadcast z (0: det_unet2D)
     pr = b.prog
     B, H, W = x.N, cfg.H, cfg.W          # images (the samples of one image share the whole U-Net)
     enc = []

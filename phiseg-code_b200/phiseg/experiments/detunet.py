@@ -1,5 +1,5 @@
-"""detunet (reference: phiseg/experiments/detunet.py): deterministic U-Net baseline.  The selectors exist so the file
-loads; phiseg_model.phiseg raises NotImplementedError for it (outside the hot-path scope)."""
+"""detunet (reference: phiseg/experiments/detunet.py): deterministic U-Net baseline (likelihoods.det_unet2D with the dummy
+posterior / prior: no latent variables, cross-entropy only)."""
 from phiseg.experiments._base import configure
 
 globals().update(configure('detunet', nets='det_unet2D', log_dir_name='lidc2', latent_levels=1, zdim0=6, annotator_range=[0],

@@ -13,4 +13,4 @@ class _Arch:
 
 phiseg = _Arch('phiseg')            # likelihoods.py: hierarchical, one latent per resolution level
 prob_unet2D = _Arch('probunet')     # likelihoods.py: Probabilistic U-Net (Kohl et al.)
-det_unet2D = _Arch('det_unet')        # likelihoods.py:10-79 deterministic U-Net (not on the hot path)
+det_unet2D = _Arch('det_unet')      # likelihoods.py:10-79: deterministic U-Net (the prob. U-Net's U-Net without z)

@@ -41,11 +41,13 @@ def net_config_from_experiment(exp, mode):
     """Reads the attributes phiseg_model.py:20-141 reads from exp_config."""
     archs = {getattr(exp.posterior, 'arch', None), getattr(exp.prior, 'arch', None),
              getattr(exp.likelihood, 'arch', None)}
+    if archs == {'dummy', 'det_unet'} and getattr(exp.likelihood, 'arch', None) == 'det_unet':
+        archs = {'det_unet'}            # experiments/detunet.py: posteriors.dummy, priors.dummy, likelihoods.det_unet2D
     if len(archs) != 1 or None in archs:
         raise ValueError('posterior/prior/likelihood must name one architecture, got %r' % (archs,))
     arch = archs.pop()
-    if arch not in ('phiseg', 'probunet'):
-        raise NotImplementedError('architecture %r is outside the B200 hot path (phiseg and prob_unet2D are built)' % arch)
+    if arch not in ('phiseg', 'probunet', 'det_unet'):
+        raise NotImplementedError('architecture %r is not built (phiseg, prob_unet2D and det_unet2D are)' % arch)
 
     def opt(name):
         return getattr(exp, name) if hasattr(exp, name) and getattr(exp, name) is not None else None

@@ -19,6 +19,8 @@ def _build(E, arch, kind, size=64, B=2, norm='batch_norm', nlabels=2):
     kw = dict(arch=arch, image_size=(size, size, 1), mode='fast', norm=norm, nlabels=nlabels)
     if arch == 'probunet':
         kw.update(zdim0=6, latent_levels=1)
+    if arch == 'det_unet':
+        kw.update(zdim0=6, latent_levels=1, KL_weight=None)
     cfg = E.NetConfig(**kw)
     P = E.Params(cfg, torch.device('cpu'))
     return cfg, P, E.build_program(cfg, P, B, kind, torch.device('cpu'))
@@ -56,7 +58,9 @@ def _check_lanes(steps):
 @pytest.mark.parametrize('arch,kind,norm', [('phiseg', 'train', 'batch_norm'), ('phiseg', 'train', 'group_norm'),
                                             ('phiseg', 'eval', 'batch_norm'), ('phiseg', 'sample', 'batch_norm'),
                                             ('phiseg', 'posterior', 'group_norm'), ('phiseg', 'from_z', 'batch_norm'),
-                                            ('probunet', 'train', 'batch_norm'), ('probunet', 'sample', 'group_norm')])
+                                            ('probunet', 'train', 'batch_norm'), ('probunet', 'sample', 'group_norm'),
+                                            ('det_unet', 'train', 'batch_norm'), ('det_unet', 'sample', 'batch_norm'),
+                                            ('det_unet', 'eval', 'group_norm')])
 def test_programs_keep_lane_discipline(E, arch, kind, norm):
     cfg, P, sp = _build(E, arch, kind, norm=norm)
     _check_lanes(sp.prog.steps)
@@ -237,16 +241,16 @@ def test_algorithmic_flops_match_the_survey(E):
 
 
 @pytest.mark.parametrize('arch,norm', [('phiseg', 'batch_norm'), ('phiseg', 'group_norm'), ('probunet', 'batch_norm'),
-                                       ('probunet', 'group_norm')])
+                                       ('probunet', 'group_norm'), ('det_unet', 'batch_norm'), ('det_unet', 'group_norm')])
 def test_variable_set_matches_the_oracle(E, oracle, arch, norm):
     """Same TF variable names and shapes in the engine's flat parameter buffer and in the oracle's parameter dict
     (checkpoints and set_weights / get_weights rely on it), and the SURVEY's parameter count for phiseg_7_5."""
     kw = dict(arch=arch, image_size=(128, 128, 1), mode='parity', norm=norm)
-    if arch == 'probunet':
+    if arch in ('probunet', 'det_unet'):
         kw.update(zdim0=6, latent_levels=1)
     cfg = E.NetConfig(**kw)
     spec = {n: tuple(shape) for n, shape, kind in E.build_spec(cfg)}
-    okw = dict(zdim0=6, latent_levels=1) if arch == 'probunet' else {}
+    okw = dict(zdim0=6, latent_levels=1) if arch in ('probunet', 'det_unet') else {}
     orc = oracle.Oracle(arch, image_size=(128, 128, 1), norm=norm, **okw)
     P = orc.init_params(seed=1)
     assert set(spec) == set(P), sorted(set(spec) ^ set(P))[:8]
@@ -306,3 +310,21 @@ def test_inference_batch_norm_folds_into_the_convolution(E, monkeypatch, arch, k
     for a, k, n in (('phiseg', 'train', 'batch_norm'), ('phiseg', 'sample', 'group_norm')):
         cfg, P, sp = _build(E, a, k, norm=n)
         assert not any(s[2] == 'phs_conv2d_post' for s in sp.prog.steps)
+
+
+def test_det_unet_program(E):
+    """likelihoods.det_unet2D (likelihoods.py:10-79) with the dummy posterior / prior (experiments/detunet.py): the
+    probabilistic U-Net's U-Net without encoders and without z - 3 * 7 encoder + 3 * 6 decoder + 3 recombination convs +
+    the prediction head, one cross-entropy level, no latent kernels, every convolution with its filter gradient."""
+    cfg, P, sp = _build(E, 'det_unet', 'train', size=128)
+    c = collections.Counter(s[2] for s in sp.prog.steps if s[0] is not None)
+    n_conv = 3 * 7 + 3 * 6 + 3 + 1
+    assert c['phs_conv2d_wgrad'] == n_conv
+    assert c['phs_latent_fwd'] == 0 and c['phs_latent_bwd'] == 0 and c['phs_xent_multiscale'] == 1
+    assert not any(n.startswith(('posterior/', 'prior/')) for n in P.table)
+    assert len(sp.eps) == 0 and len(sp.logits) == 1 and sp.logits[0].C == 2
+    assert cfg.latent_shapes(3) == []
+    # FLOPs: the probabilistic U-Net's likelihood minus the z channels of recomb_0
+    cfg2, P2, sp2 = _build(E, 'probunet', 'eval', size=128, B=1)
+    cfg1, P1, sp1 = _build(E, 'det_unet', 'eval', size=128, B=1)
+    assert 0.65 < sp1.conv_flop_fwd / sp2.conv_flop_fwd < 0.85       # (the other 25 % are the posterior and prior encoders)

@@ -34,8 +34,8 @@ def _setup(pkg, oracle, exp_name, B, mode='parity', graph=False, size=SIZE, seed
     model = pm.phiseg(exp, mode=mode, use_cuda_graph=graph)
     cfg = model.cfg
     orc = oracle.Oracle(cfg.arch, image_size=(size, size, 1), nlabels=cfg.nlabels, zdim0=cfg.zdim0, n0=cfg.n0,
-                        resolution_levels=cfg.R, latent_levels=cfg.L, norm=cfg.norm,
-                        dtype=torch.float64 if fp64 else torch.float32)
+                        resolution_levels=cfg.R, latent_levels=cfg.L, norm=cfg.norm, KL_weight=cfg.KL_weight,
+                        xent_weight=cfg.xent_weight, dtype=torch.float64 if fp64 else torch.float32)
     P = orc.init_params(seed=seed)
     model.set_weights({k: v.numpy() for k, v in P.items()})
     x, s = oracle.synthetic_batch(B, size, size, cfg.nlabels, seed=3)
@@ -51,7 +51,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize('exp_name,mode,tol_loss,tol_grad', [
     ('phiseg_7_5_gn', 'parity', 1e-4, 5e-3), ('phiseg_7_5', 'parity', 1e-3, 5e-1), ('probunet', 'parity', 1e-3, 5e-1),
-    ('phiseg_7_1', 'parity', 1e-3, 5e-1),
+    ('phiseg_7_1', 'parity', 1e-3, 5e-1), ('detunet', 'parity', 1e-3, 5e-1), ('detunet+gn', 'parity', 1e-4, 5e-3),
     # the same contract on the tensor cores: three bf16 tcgen05 passes over a (hi, lo) operand split per convolution
     # (measured round 2: 4.1e-3 / 5.8e-1 / 5.7e-3 against 3.9e-3 / 1.8e-1 / - for the CUDA-core mode)
     ('phiseg_7_5_gn', 'parity_tc', 1e-4, 1e-2), ('phiseg_7_5', 'parity_tc', 1e-3, 1.0), ('probunet+gn', 'parity_tc', 1e-4, 1e-2)])
@@ -238,7 +238,7 @@ def test_training_step_full_size(pkg, oracle, exp_name, size, B, mode, tol_loss,
         assert gcos > 0.3, gcos
 
 
-@pytest.mark.parametrize('exp_name,size', [('phiseg_7_5_gn', 64), ('phiseg_7_5', 128), ('probunet', 128)])
+@pytest.mark.parametrize('exp_name,size', [('phiseg_7_5_gn', 64), ('phiseg_7_5', 128), ('probunet', 128), ('detunet', 128)])
 def test_sampling_fast_mode(pkg, oracle, exp_name, size):
     """What bf16 costs on the sampling path (SURVEY.md D6 asks for the measured tolerance next to the fast number): the
     summed logits of one prior sample against the fp64 oracle.  The north-star contract (1e-3 per logit, exact argmax) is

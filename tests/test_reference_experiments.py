@@ -9,7 +9,7 @@ import os
 import pytest
 
 REF = '/root/reference/phiseg/experiments'
-NAMES = ['phiseg_7_5', 'phiseg_7_1', 'probunet', 'phiseg_7_5_1annot', 'phiseg_7_1_1annot', 'probunet_1annot']
+NAMES = ['phiseg_7_5', 'phiseg_7_1', 'probunet', 'phiseg_7_5_1annot', 'phiseg_7_1_1annot', 'probunet_1annot', 'detunet']
 
 
 def _public(mod):
@@ -136,7 +136,8 @@ def test_variable_names_follow_the_reference_scopes(pkg):
         return any(r.match(part) for r in regs)
 
     norm_tail = {'batch_norm', 'BatchNorm', 'group_norm', 'W', 'b', 'beta', 'gamma', 'moving_mean', 'moving_variance'}
-    for arch, kw in (('phiseg', {}), ('probunet', dict(zdim0=6, latent_levels=1))):
+    for arch, kw in (('phiseg', {}), ('probunet', dict(zdim0=6, latent_levels=1)),
+                     ('det_unet', dict(zdim0=6, latent_levels=1, KL_weight=None))):
         cfg = eng.NetConfig(arch=arch, image_size=(128, 128, 1), mode='parity', norm='batch_norm', **kw)
         for name, shape, kind in eng.build_spec(cfg):
             parts = name.split('/')
