@@ -1,16 +1,6 @@
-"""Architecture selectors with the reference's names (phiseg/model_zoo/posteriors.py).  An experiment file assigns one of
-these to `posterior`; the topology itself is laid down by engine.build_program."""
+"""phiseg/model_zoo/posteriors.py selectors (see model_zoo/__init__.py)."""
+from . import Arch
 
-
-class _Arch:
-    def __init__(self, arch):
-        self.arch = arch
-        self.__name__ = arch
-
-    def __repr__(self):
-        return '<posteriors.%s>' % self.arch
-
-
-phiseg = _Arch('phiseg')            # posteriors.py: hierarchical, one latent per resolution level
-prob_unet2D = _Arch('probunet')     # posteriors.py: Probabilistic U-Net (Kohl et al.)
-dummy = _Arch('dummy')                # posteriors.py: placeholder used by detunet
+phiseg = Arch('posteriors', 'phiseg', 'phiseg')              # posteriors.py:56-132: hierarchical, one latent per level
+prob_unet2D = Arch('posteriors', 'prob_unet2D', 'probunet')  # posteriors.py:9-53: Probabilistic U-Net (Kohl et al.)
+dummy = Arch('posteriors', 'dummy', 'dummy')                 # posteriors.py:135-138: placeholder used by detunet

@@ -1,16 +1,6 @@
-"""Architecture selectors with the reference's names (phiseg/model_zoo/priors.py).  An experiment file assigns one of
-these to `prior`; the topology itself is laid down by engine.build_program."""
+"""phiseg/model_zoo/priors.py selectors (see model_zoo/__init__.py)."""
+from . import Arch
 
-
-class _Arch:
-    def __init__(self, arch):
-        self.arch = arch
-        self.__name__ = arch
-
-    def __repr__(self):
-        return '<priors.%s>' % self.arch
-
-
-phiseg = _Arch('phiseg')            # priors.py: hierarchical, one latent per resolution level
-prob_unet2D = _Arch('probunet')     # priors.py: Probabilistic U-Net (Kohl et al.)
-dummy = _Arch('dummy')                # priors.py: placeholder used by detunet
+phiseg = Arch('priors', 'phiseg', 'phiseg')                  # priors.py:51-128
+prob_unet2D = Arch('priors', 'prob_unet2D', 'probunet')      # priors.py:8-48
+dummy = Arch('priors', 'dummy', 'dummy')                     # priors.py:130-133
