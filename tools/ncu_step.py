@@ -13,6 +13,8 @@ def main():
     ap.add_argument('--config', default='phiseg_7_5')
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--out', default='gpurun_out/step_list.json')
+    ap.add_argument('--kind', default='train', choices=['train', 'sample'],
+                    help="'sample': one pass of the sampling program (prior encoder + one noise draw of 64 rows) instead")
     args = ap.parse_args()
     os.environ['PHS_NO_LANES'] = '1'
     import ctypes
@@ -25,9 +27,13 @@ def main():
     model = pm.phiseg(exp, mode='fast', use_cuda_graph=False)
     import importlib as _il; o = _il.import_module("phiseg_code_b200.data")
     x, s = o.synthetic_batch(args.batch, model.cfg.H, model.cfg.W, model.cfg.nlabels, seed=1)
-    for _ in range(2):
-        model.training_step(x, s, 1e-3)
-    sp = model._program('train', args.batch)
+    if args.kind == 'sample':
+        model.predict(x, num_samples=2)
+        sp = model._program('sample', args.batch)
+    else:
+        for _ in range(2):
+            model.training_step(x, s, 1e-3)
+        sp = model._program('train', args.batch)
     st = torch.cuda.current_stream().cuda_stream
     steps = [s_ for s_ in sp.prog.steps if s_[0] is not None]
 
