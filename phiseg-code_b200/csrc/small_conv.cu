@@ -22,12 +22,50 @@ __device__ __forceinline__ float wsel(const float* __restrict__ w, const SmallGe
   return w[((size_t)(taps - 1 - t) * g.Cout + b) * g.Cin + a];   // dgrad: in = dy (co), out = dx (ci), taps flipped
 }
 
+// 8 consecutive channels as loaded (16 bytes of bf16 / 32 bytes of float): unpacked only where they are consumed, so that
+// several vectors per thread can be in flight without the unpacked copies filling the register file
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float* v) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 // ---- wide input -> NOUT <= 8 outputs ----------------------------------------------------------------------------
 // TPP threads share a pixel (each takes every TPP-th 8-channel vector), partial dot products are combined by shuffles.
 // ksize 1: a thread's channels never change, so its filter slice lives in registers (MAXV vectors per thread);
 // ksize 3: compact [tap][Cin][NOUT] filter copy in shared memory.
+// The ksize-1 heads are pure streaming: what bounds them is bytes in flight (round 2, ncu: 64x64 192->2 at 1.5 TB/s with 95
+// registers = 2 blocks per SM and MAXV loads per thread outstanding, long_scoreboard 10 warps per issue).  A thread
+// therefore takes UP pixel groups per iteration and issues all their loads first (6-8 outstanding 16-byte loads), the grid
+// is one wave of two resident blocks per SM.
+constexpr int small_cout_up(int maxv, int nout) {      // pixel groups per iteration that fit next to the filter registers
+  const int wr = maxv * 8 * nout, per = maxv * 8;
+  const int up = per > 0 && wr < 96 ? (96 - wr) / per : 1;
+  return up < 1 ? 1 : (up > 4 ? 4 : up);
+}
 template <typename TI, typename TO, int TPP, int NOUT, int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXV > 0 ? (MAXV * 8 * NOUT <= 64 ? 2 : 1) : (NOUT <= 2 ? 3 : 2))
     small_cout_kernel(const TI* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       TO* __restrict__ y, SmallGeom g, int accumulate) {
   PHS_PDL_PROLOGUE();
@@ -48,14 +86,72 @@ __global__ void __launch_bounds__(256)
           wr[j][i][o] = (cv < nvec && o < g.Cout) ? wsel(w, g, 0, cv * 8 + i, o) : 0.f;
     }
   } else {
+    // [tap][vector][8 channels x NOUT + 4 floats of padding]: the TPP threads of a pixel read consecutive vectors with
+    // 16-byte loads; the padded stride (80 / 144 / 272 bytes) puts them on distinct banks (round 2, ncu of the unpadded
+    // scalar reads: 6.9 M bank conflicts in 9.4 M shared-memory wavefronts, mio_throttle the dominant stall)
+    constexpr int VS = 8 * NOUT + 4;
     for (int i = threadIdx.x; i < taps * g.Cin * NOUT; i += blockDim.x) {
       int o = i % NOUT, a = (i / NOUT) % g.Cin, t = (i / NOUT) / g.Cin;
-      ws[i] = o < g.Cout ? wsel(w, g, t, a, o) : 0.f;
+      ws[(size_t)(t * nvec + a / 8) * VS + (a % 8) * NOUT + o] = o < g.Cout ? wsel(w, g, t, a, o) : 0.f;
     }
     __syncthreads();
   }
   const int64_t M = (int64_t)g.N * g.H * g.W;
   const int pad = g.ks / 2;
+  if (MAXV > 0) {
+    constexpr int UP = small_cout_up(MAXV, NOUT);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // (block-uniform loop bound: every lane takes part in the shuffles)
+    // unconditional loads: a vector index beyond the tensor is clamped (its filter registers are zero), a pixel beyond the
+    // end is clamped and not stored - no branch separates the loads, so all UP * MAXV of them are issued back to back
+    int cvoff[MV];
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) cvoff[j] = (sub + j * TPP < nvec ? sub + j * TPP : nvec - 1) * 8;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < M * TPP; base += UP * stride) {
+      Raw8<TI> raw[UP][MV];
+      int64_t pixs[UP];
+      bool lives[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        const int64_t pix_raw = (base + u * stride + threadIdx.x) / TPP;
+        lives[u] = pix_raw < M;
+        pixs[u] = lives[u] ? pix_raw : M - 1;
+        const TI* px = x + pixs[u] * g.ldx;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) raw[u][j].load(px + cvoff[j]);
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        float acc[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+          float v[8];
+          raw[u][j].unpack(v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(v[i], wr[j][i][o], acc[o]);
+        }
+#pragma unroll
+        for (int off = TPP / 2; off > 0; off >>= 1)
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+        if (sub == 0 && lives[u]) {
+          TO* py = y + pixs[u] * g.ldy;
+#pragma unroll
+          for (int o = 0; o < NOUT; ++o)
+            if (o < g.Cout) {
+              float r = acc[o] + (bias ? bias[o] : 0.f);
+              if (accumulate) r += ldf<TO>(py + o);
+              stf<TO>(py + o, r);
+            }
+        }
+      }
+    }
+    return;
+  }
   // the loop bound is block-uniform: every lane takes part in the shuffles below
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < M * TPP; base += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix_raw = (base + threadIdx.x) / TPP;
@@ -85,14 +181,29 @@ __global__ void __launch_bounds__(256)
         const int hh = hq + t / g.ks - pad, ww = wq + t % g.ks - pad;
         if (hh < 0 || hh >= g.H || ww < 0 || ww >= g.W) continue;
         const TI* px = x + (pix + (int64_t)(hh - hq) * g.W + (ww - wq)) * g.ldx;
-        const float* wt = ws + (size_t)t * g.Cin * NOUT;
-        for (int cv = sub; cv < nvec; cv += TPP) {
-          float v[8];
-          ldv<TI, 8>(px + cv * 8, v);
+        constexpr int VS = 8 * NOUT + 4;
+        const float* wt = ws + (size_t)t * nvec * VS;
+        for (int cv0 = sub; cv0 < nvec; cv0 += 4 * TPP) {
+          Raw8<TI> raw[4];        // up to four of this thread's vectors in flight (index clamped: no branch between the loads)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int j = 0; j < 4; ++j) raw[j].load(px + (cv0 + j * TPP < nvec ? cv0 + j * TPP : nvec - 1) * 8);
 #pragma unroll
-            for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(v[i], wt[(cv * 8 + i) * NOUT + o], acc[o]);
+          for (int j = 0; j < 4; ++j)
+            if (cv0 + j * TPP < nvec) {
+              float v[8];
+              raw[j].unpack(v);
+              const float4* wv = reinterpret_cast<const float4*>(wt + (size_t)(cv0 + j * TPP) * VS);
+              float wreg[8 * NOUT];
+#pragma unroll
+              for (int q = 0; q < 2 * NOUT; ++q) {
+                const float4 f = wv[q];
+                wreg[4 * q] = f.x; wreg[4 * q + 1] = f.y; wreg[4 * q + 2] = f.z; wreg[4 * q + 3] = f.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(v[i], wreg[i * NOUT + o], acc[o]);
+            }
         }
       }
     }
@@ -299,8 +410,10 @@ __global__ void __launch_bounds__(256)
 
 // ---- filter gradient of a 1x1 head (wide x, NS <= 8 output channels): dW[ci][co] = sum_p x[p][ci] * dy[p][co] -------
 // thread <-> (8-channel vector of x, pixel lane) and ALL output channels: the 16-byte x load is shared by NS FMAs x 8.
+// (round 2, ncu: 128x128 128->2 at 1.9 TB/s with four loads per thread outstanding and 592 blocks on 444 resident slots:
+// eight loads in flight for NS <= 2 and one wave of two resident blocks per SM)
 template <typename TW, typename TS, int NS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NS <= 4 ? 2 : 1)
     wgrad_head_kernel(const TW* __restrict__ x, int ldx, int Cw, const TS* __restrict__ dy, int lds, int Cs, int64_t M,
                       int64_t pix_per_block, float* __restrict__ dw) {
   PHS_PDL_PROLOGUE();
@@ -318,29 +431,32 @@ __global__ void __launch_bounds__(256)
   if (lp < PL) {
     const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
     const int64_t p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
-    constexpr int U = 4;
+    constexpr int U = NS <= 2 ? 8 : 4;
     for (int64_t p = p0 + lp; p < p1; p += (int64_t)U * PL) {
-      float v[U][8], d[U][NS];
+      // unconditional loads (a pixel beyond the range is clamped and its dy taken as zero): no branch between them
+      Raw8<TW> raw[U];
+      float d[U][NS];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t q = p + (int64_t)u * PL;
-        if (q < p1) {
-          ldv<TW, 8>(x + q * ldx + cv * 8, v[u]);
+        const bool in = q < p1;
+        const int64_t qc = in ? q : p1 - 1;
+        raw[u].load(x + qc * ldx + cv * 8);
 #pragma unroll
-          for (int s = 0; s < NS; ++s) d[u][s] = s < Cs ? ldf<TS>(dy + q * lds + s) : 0.f;
-        } else {
-#pragma unroll
-          for (int o = 0; o < 8; ++o) v[u][o] = 0.f;
-#pragma unroll
-          for (int s = 0; s < NS; ++s) d[u][s] = 0.f;
+        for (int s = 0; s < NS; ++s) {
+          const float t = s < Cs ? ldf<TS>(dy + qc * lds + s) : 0.f;
+          d[u][s] = in ? t : 0.f;
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u) {
+        float v[8];
+        raw[u].unpack(v);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
-          for (int o = 0; o < 8; ++o) acc[s][o] = fmaf(d[u][s], v[u][o], acc[s][o]);
+          for (int o = 0; o < 8; ++o) acc[s][o] = fmaf(d[u][s], v[o], acc[s][o]);
+      }
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -367,7 +483,7 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
   const int xes = x->dtype == PHS_BF16 ? 2 : 4, yes = y->dtype == PHS_BF16 ? 2 : 4;
   if (y->C <= 8 && x->C % 8 == 0 && x->C >= 8 && x->ld % 8 == 0 && ((uintptr_t)x->ptr % (8 * xes > 16 ? 16 : 8 * xes)) == 0) {
     const int nout = y->C <= 2 ? 2 : y->C <= 4 ? 4 : 8;
-    const size_t smem = ksize == 1 ? 0 : (size_t)taps * x->C * nout * sizeof(float);
+    const size_t smem = ksize == 1 ? 0 : (size_t)taps * (x->C / 8) * (8 * nout + 4) * sizeof(float);   // padded, see the kernel
     if (smem > 48 * 1024) return 0;
     const int nvec = x->C / 8;
     const int tpp = nvec >= 8 ? 8 : nvec >= 4 ? 4 : nvec >= 2 ? 2 : 1;
@@ -375,6 +491,8 @@ int small_conv_try(const phs_tensor* x, const float* w, const float* bias, const
     if (ksize == 1 && (maxv > 4 || (nout == 8 && maxv > 2))) return 0;
     int64_t blocks = (M * tpp + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (ksize == 1 && blocks > 148 * 2) blocks = 148 * 2;      // one wave of the two resident blocks per SM
+    if (ksize != 1 && blocks > 148 * 6) blocks = 148 * 6;      // two waves of the three resident blocks
 #define LAUNCH_K(TI, TO, TPPV, NOUTV, MAXVV) \
   phs_launch(small_cout_kernel<TI, TO, TPPV, NOUTV, MAXVV>, (int)blocks, 256, smem, st, (const TI*)x->ptr, w, bias, (TO*)y->ptr, g, accumulate)
 #define LAUNCH_V(TI, TO, TPPV, NOUTV)                          \
@@ -465,7 +583,7 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
   if (!small_is_x && wd->C / 8 <= 32) {
     // 1x1 head: one thread per (x vector, pixel lane) for all output channels
     const int nvec = wd->C / 8;
-    int64_t splits = 148 * 4;
+    int64_t splits = s->C <= 4 ? 148 * 2 : 148;
     if (splits > (M + 255) / 256) splits = (M + 255) / 256;
     if (splits < 1) splits = 1;
     const int64_t ppb = (M + splits - 1) / splits;

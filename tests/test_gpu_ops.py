@@ -457,3 +457,29 @@ def test_im2col3x3(call, lib, oracle, Cin, Co, dt):
     assert float(col[..., 9 * Cin:].float().abs().max()) == 0.0
     # exactness of the gather itself: centre tap reproduces x
     assert torch.equal(col[..., 4 * Cin:5 * Cin].float().cpu(), x.to(torch.bfloat16).float())
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout', [(2, 32, 32, 128, 2), (3, 16, 16, 192, 2), (1, 16, 24, 256, 2), (2, 16, 16, 64, 4),
+                                            (2, 8, 8, 32, 6), (5, 7, 9, 128, 2), (2, 16, 16, 96, 4), (2, 128, 128, 32, 2)])
+@pytest.mark.parametrize('xdt', [torch.bfloat16, torch.float32])
+def test_head_1x1_streaming_kernels(call, lib, oracle, N, H, W, Cin, Cout, xdt):
+    """The 1x1 heads (z*_mu / z*_sigma / y_lvl* / prediction, posteriors.py:105-128, likelihoods.py:218) and their filter
+    gradient: register-resident filters, several pixel groups per thread in flight, one-wave grids - every unroll / tail
+    combination (pixel counts that do not divide the grid stride, 1..4 vectors per thread, 2 / 4 / 8 output lanes)."""
+    g = torch.Generator().manual_seed(N * 100 + Cin + Cout + H)
+    x = torch.randn(N, H, W, Cin, generator=g).to(xdt)
+    w = torch.randn(1, 1, Cin, Cout, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    xr = x.double()
+    ref = oracle.conv2d_same(xr, w.double(), b.double())
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    yd = torch.full((N, H, W, Cout), 3.0, device='cuda')
+    call('phs_conv2d', call.T(xd), wd, bd, call.T(yd), 1, 0, 0, lib.IMPL_SIMT)
+    close(yd, ref, what='1x1 head fwd', rtol=2e-5)
+    call('phs_conv2d', call.T(xd), wd, None, call.T(yd), 1, 0, 1, lib.IMPL_SIMT)
+    close(yd, 2 * ref - b.double(), what='1x1 head fwd accumulate', rtol=2e-5)
+    gy = torch.randn(N, H, W, Cout, generator=g)
+    gw_ref = torch.einsum('nhwc,nhwo->co', xr, gy.double()).reshape(1, 1, Cin, Cout)
+    gwd = torch.zeros_like(wd)
+    call('phs_conv2d_wgrad', call.T(xd), call.T(gy.cuda()), gwd, None, 1, 0, lib.IMPL_SIMT)
+    close(gwd, gw_ref, what='1x1 head wgrad', rtol=5e-5)
