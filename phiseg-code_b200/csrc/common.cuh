@@ -175,6 +175,35 @@ __device__ __forceinline__ void stv(T* p, const float* in) {
   }
 }
 
+// 8 consecutive channels as loaded (16 bytes of bf16 / 32 bytes of float): unpacked only where they are consumed, so that
+// several vectors per thread can be in flight without the unpacked copies filling the register file
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float* v) const {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <>
+struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float* v) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
 // ---- normalisation arithmetic shared by every kernel that applies batch_norm / group_norm2D + ReLU -----------------
 // (tfwrapper/normalisation.py:17-36,145-163, tfwrapper/layers.py:134-135).  The activation a = act(gamma*(y-mean)*rstd +
 // beta) is produced in three places - the stand-alone norm_act kernels, the operand transform of the fused convolution

@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(RED_THREADS) chan_stats_kernel(const T* __rest
 // REMAT: also write the activation (a_out).  Same grid and the same summation order as the plain variant (the partial
 // sums, and with them every bit downstream, do not depend on which variant ran); two loads in flight instead of four keep
 // it at three blocks per SM without spills.
-template <typename T, int V, bool REMAT>
-__global__ void __launch_bounds__(RED_THREADS, 3)
+// RAWL (V == 8, not with REMAT): the four (g, y) vector pairs stay packed in registers until used - eight loads in flight per
+// thread instead of two (see norm_bwd_apply_kernel), two blocks per SM.
+template <typename T, int V, bool REMAT, bool RAWL = false>
+__global__ void __launch_bounds__(RED_THREADS, RAWL ? 2 : 3)
     norm_bwd_reduce_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, int HW, int C,
                            int pix_per_block, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
@@ -107,6 +109,31 @@ __global__ void __launch_bounds__(RED_THREADS, 3)
     if (lane_p < PL) {
       constexpr int U = REMAT ? 2 : 4;
       int p = p0 + lane_p;
+      if constexpr (RAWL) {
+        static_assert(V == 8 && !REMAT, "packed loads: 8-channel vectors, plain reduction");
+        for (; p + (U - 1) * PL < p1; p += U * PL) {
+          Raw8<T> graw[U], yraw[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            graw[u].load(gb + (size_t)(p + u * PL) * ldg + cv * V);
+            yraw[u].load(yb + (size_t)(p + u * PL) * ldy + cv * V);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float gv[V], yv[V];
+            graw[u].unpack(gv);
+            yraw[u].unpack(yv);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+              float xh = (yv[i] - mu[i]) * rs[i];
+              float a = ga[i] * xh + be[i];
+              float gm = (relu && a <= 0.f) ? 0.f : gv[i];
+              s1[i] += gm;
+              s2[i] += gm * xh;
+            }
+          }
+        }
+      }
       for (; p + (U - 1) * PL < p1; p += U * PL) {
         float gv[U][V], yv[U][V];
 #pragma unroll
@@ -179,6 +206,12 @@ static int norm_bps_override() {
   return e ? atoi(e) : 0;
 }
 
+// PHS_NORM_RAW=0: the pre-round-2 load scheduling of the backward normalisation kernels (A/B switch, read per call)
+static bool norm_raw_loads() {
+  const char* e = getenv("PHS_NORM_RAW");
+  return !(e && e[0] == '0');
+}
+
 static int pick_chunks(int N, int slots, int max_chunks) {
   if (norm_bps_override() > 0) slots = 148 * norm_bps_override();
   int chunks = slots / N;
@@ -232,9 +265,14 @@ static int norm_bwd_reduce_run(const char* fn, const phs_tensor* g, const phs_te
   int v = min_vec(pick_vec(y), pick_vec(g));
   if (a) v = min_vec(v, pick_vec(a));
   dim3 grid; int ppb; size_t smem;
-  red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem);
+  const bool rawl = !a && v == 8 && norm_raw_loads();
+  red_geometry(y->N, HW, y->C, v, &grid, &ppb, &smem, rawl ? 2 : 3);
   PHS_REQUIRE(smem <= 48 * 1024, "%s: C=%d too large", fn, y->C);
-  if (a) {
+  if (rawl) {
+    PHS_DISPATCH_DTYPE(y->dtype, T, (phs_launch(norm_bwd_reduce_kernel<T, 8, false, true>, grid, RED_THREADS, smem, st,
+                                                (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean, rstd,
+                                                gamma, beta, relu, sums, 1, (T*)nullptr, 0)));
+  } else if (a) {
     PHS_DISPATCH_DTYPE(y->dtype, T,
                        PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_reduce_kernel<T, V, true>, grid, RED_THREADS, smem, st,
                                                   (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, HW, y->C, ppb, mean,
@@ -612,8 +650,11 @@ struct BnTotals {
   int accumulate;
 };
 
-template <typename T, int V>
-__global__ void __launch_bounds__(256, 3)
+// RAWL (bf16 / float, V == 8): the STREAM_U pixel vectors of g and y stay PACKED in registers until they are used, so all
+// 2 * STREAM_U loads are issued back to back (with unpacked fp32 copies next to the 7 x V per-channel coefficients ptxas
+// serialised the loads in pairs under the 85-register cap: 2 loads in flight per thread); two blocks per SM.
+template <typename T, int V, bool RAWL>
+__global__ void __launch_bounds__(256, RAWL ? 2 : 3)
     norm_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ y, int ldy, T* __restrict__ dy,
                           int lddy, int HW, int C, int pix_per_block, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -659,6 +700,31 @@ __global__ void __launch_bounds__(256, 3)
       }
     }
     int p = p0 + lane_p;
+    if constexpr (RAWL) {
+      static_assert(V == 8, "packed loads are 8-channel vectors");
+      for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
+        Raw8<T> graw[STREAM_U], yraw[STREAM_U];
+#pragma unroll
+        for (int u = 0; u < STREAM_U; ++u) {
+          graw[u].load(gb + (size_t)(p + u * PL) * ldg + cv * V);
+          yraw[u].load(yb + (size_t)(p + u * PL) * ldy + cv * V);
+        }
+#pragma unroll
+        for (int u = 0; u < STREAM_U; ++u) {
+          float gv[V], yv[V];
+          graw[u].unpack(gv);
+          yraw[u].unpack(yv);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            float xh = fmaf(yv[k], rs[k], xo[k]);
+            float aa = fmaf(yv[k], sc[k], sh[k]);
+            float gm = (relu && aa <= 0.f) ? 0.f : gv[k];
+            gv[k] = gm * gr[k] - k1[k] - xh * k2[k];
+          }
+          stv<T, V>(db + (size_t)(p + u * PL) * lddy + cv * V, gv);
+        }
+      }
+    }
     for (; p + (STREAM_U - 1) * PL < p1; p += STREAM_U * PL) {
       float gv[STREAM_U][V], yv[STREAM_U][V];
 #pragma unroll
@@ -705,11 +771,18 @@ static int norm_bwd_apply_run(const char* what, const phs_tensor* g, const phs_t
   int HW = y->H * y->W;
   bn.count = (double)HW * y->N;
   dim3 grid; int ppb;
-  stream_geometry(y->N, HW, y->C, v, 3, &grid, &ppb);
-  PHS_DISPATCH_DTYPE(y->dtype, T,
-                     PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_apply_kernel<T, V>, grid, 256, 0, (cudaStream_t)stream, 
+  const bool rawl = v == 8 && norm_raw_loads();
+  stream_geometry(y->N, HW, y->C, v, rawl ? 2 : 3, &grid, &ppb);
+  if (rawl) {
+    PHS_DISPATCH_DTYPE(y->dtype, T, (phs_launch(norm_bwd_apply_kernel<T, 8, true>, grid, 256, 0, (cudaStream_t)stream,
                                                 (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
-                                                HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef, bn))));
+                                                HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef, bn)));
+  } else {
+    PHS_DISPATCH_DTYPE(y->dtype, T,
+                       PHS_DISPATCH_VEC(v, V, (phs_launch(norm_bwd_apply_kernel<T, V, false>, grid, 256, 0, (cudaStream_t)stream,
+                                                  (const T*)g->ptr, g->ld, (const T*)y->ptr, y->ld, (T*)dy->ptr, dy->ld,
+                                                  HW, y->C, ppb, mean, rstd, gamma, beta, relu, coef, bn))));
+  }
   return phs_check_launch(what);
 }
 

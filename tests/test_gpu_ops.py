@@ -33,7 +33,9 @@ def call(lib):
 # ---------------------------------------------------------------------------------------------------------
 CONV_CASES = [  # N, H, W, Cin, Cout, k
     (2, 16, 16, 3, 32, 3), (2, 8, 8, 32, 32, 3), (1, 4, 4, 192, 192, 3), (3, 2, 2, 192, 2, 3), (2, 16, 16, 64, 2, 1),
-    (2, 32, 32, 1, 32, 3), (1, 8, 8, 70, 32, 1), (2, 16, 8, 5, 17, 3)]
+    (2, 32, 32, 1, 32, 3), (1, 8, 8, 70, 32, 1), (2, 16, 8, 5, 17, 3),
+    # the z inputs (zdim_0 = 2 channels, 3x3): the unrolled small_cin specialisation, incl. 24 output vectors and tiny images
+    (2, 16, 16, 2, 64, 3), (3, 8, 8, 2, 192, 3), (2, 2, 2, 2, 32, 3), (1, 32, 16, 2, 128, 3)]
 
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout,k', CONV_CASES)
@@ -88,6 +90,14 @@ def test_conv_mixed_dtypes(call, lib, oracle):
     call('phs_conv2d', call.T(xd), cu(w), None, call.T(yd), 3, 0, 0, lib.IMPL_SIMT)
     ref = oracle.conv2d_same(xd.float().cpu().double(), w.double())
     close(yd, ref, what='bf16 in, f32 out')
+    # f32 in (a latent sample z), bf16 out: the first convolution behind every z in fast mode
+    z = torch.randn(3, 16, 16, 2, generator=g)
+    wz = torch.randn(3, 3, 2, 64, generator=g) * 0.3
+    bz = torch.randn(64, generator=g)
+    yz = torch.empty(3, 16, 16, 64, device='cuda', dtype=torch.bfloat16)
+    call('phs_conv2d', call.T(cu(z)), cu(wz), cu(bz), call.T(yz), 3, 0, 0, lib.IMPL_SIMT)
+    refz = oracle.conv2d_same(z.double(), wz.double(), bz.double())
+    close(yz, refz, rtol=2 ** -8, what='f32 in, bf16 out (z input)')
 
 
 def test_conv_argument_errors(call, lib):

@@ -5,8 +5,11 @@ Device time of 10 graph replays after 4 warm-up steps (CUDA events); tuning numb
 import importlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import faulthandler
 import torch
 from __graft_entry__ import load_package
+if os.environ.get('AB_WATCHDOG'):          # dump the Python stack if a setting has not finished after that many seconds
+    faulthandler.dump_traceback_later(int(os.environ['AB_WATCHDOG']), repeat=False, exit=True)
 load_package()
 pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
 ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
