@@ -160,6 +160,11 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 900) dumps its Python stacks and exits -
+    # a stuck launch must end as a failed run with a traceback, never as a box that hangs until an outer limit kills it
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '900')), repeat=False, exit=True)
+
     import numpy as np
     import torch
     from __graft_entry__ import load_package
@@ -231,6 +236,9 @@ def main():
     if world > 1:
         torch.distributed.barrier()
     dt_e2e = parallel.max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, t_host), dev)
+    # bytes the e2e steps above copied per step, counted by training_step from the tensors it copies (read NOW: the
+    # input-pipeline leg further down feeds device-resident batches, which copy nothing from the host)
+    e2e_h2d, e2e_d2h = int(model.h2d_bytes), int(model.d2h_bytes)
     clk = clocks.stop() if rank == 0 else None
 
     # ---- sampling (img*samples/s): predict()'s device work for SAMPLES prior samples of every image of the
@@ -256,7 +264,8 @@ def main():
         samp = {'value': batch * SAMPLES / dt_s, 'unit': 'image*samples/s', 'samples_per_image': SAMPLES,
                 'ms_per_sample_pass': dt_s / SAMPLES * 1e3, 'gpu_launches': model.gpu_launches - l0,
                 'what': 'phiseg.predict(x_host[%d], num_samples=%d) -> host masks: prior encoder once per image, latent '
-                        'hierarchy + likelihood once per sample, accumulation / argmax on device' % (batch, SAMPLES),
+                        'hierarchy + likelihood once per sample, inference-mode batch norm folded into the convolution '
+                        'epilogues, accumulation / argmax on device' % (batch, SAMPLES),
                 'mask_sum': int(seg.sum())}
 
     # ---- input pipeline: the device-resident batch provider alone (host draws the reference's random
@@ -342,7 +351,7 @@ def main():
         'loss': loss_dev,
         'clocks': clk,
         'e2e': {'value': world * batch * args.steps / dt_e2e, 'unit': 'images/s',
-                'h2d_bytes_per_step': int(model.h2d_bytes), 'd2h_bytes_per_step': int(model.d2h_bytes),
+                'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': e2e_d2h,
                 'ms_per_step': dt_e2e / args.steps * 1e3},
         'sampling': samp,
         'input_pipeline': feed,

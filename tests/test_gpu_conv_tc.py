@@ -215,7 +215,11 @@ def test_conv_tc_fused_statistics(call, lib, oracle, N, H, W, Cin, Cout):
     # accumulating variant (the engine clears one arena for all layers): adds onto what the caller left in stats
     acc = torch.zeros(N + 1, Cout, 2, device='cuda', dtype=torch.float64)    # per-sample sums + the [C][2] batch totals
     call('phs_conv2d_stats_acc', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, acc)
-    assert relerr(acc[:N], stats) < 1e-4
-    assert relerr(acc[N], stats.sum(dim=0)) < 1e-4
+    # few-tile layers (fewer than PHS_STATS_MIN_HW = 2048 pixels per image): phs_conv2d_stats_acc takes its statistics from a
+    # separate pass over the bf16-rounded output, phs_conv2d_stats from the fp32 accumulators - bf16 rounding apart
+    tol = 5e-3 if H * W < 2048 else 1e-4
+    assert relerr(acc[:N], stats) < tol
+    assert relerr(acc[N], stats.sum(dim=0)) < tol
     call('phs_conv2d_stats_acc', call.T(x.cuda()), wf, b.cuda(), call.T(yb), 3, acc)
-    assert relerr(acc[:N], 2 * stats) < 1e-4 and relerr(acc[N], 2 * stats.sum(dim=0)) < 1e-4
+    assert relerr(acc[:N], 2 * stats) < tol and relerr(acc[N], 2 * stats.sum(dim=0)) < tol
+    assert relerr(acc[N], acc[:N].sum(dim=0)) < 1e-9          # the batch totals are the sum of the per-sample sums
