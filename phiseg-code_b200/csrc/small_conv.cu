@@ -4,6 +4,7 @@
 // and the gradients of both.  These are dot products of a few hundred terms per pixel: no tensor cores, the job is to
 // stream the wide tensor once with 16-byte accesses.  fp32 master filters (HWIO), fp32 accumulation, any mix of
 // float32 / bfloat16 activations.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -404,6 +405,94 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---- 3x3 filter gradient, small side = x with CS <= 2 channels (the z inputs: z*_post_1, z*_ups_to_*_c_1) --------------
+//   dW[t][cs][cw] = sum_p x[p + t][cs] * dy[p][cw]
+// thread <-> (8-channel vector of dy, cs, pixel lane) with ALL NINE taps in registers (72 accumulators): the wide vector is
+// loaded once per (pixel, cs) instead of once per (pixel, cs, tap) - the generic kernel above re-read dy 18 times through
+// L1 (round 2, ncu: 84 us for an 8 MB tensor, LSU / issue bound).  Two pixels per iteration, loads first.  The pixel lanes
+// of a block are combined in shared memory one lane at a time (plain read-modify-write: shared fp32 atomics are CAS
+// loops), blocks with global atomics.
+template <typename TS, typename TW, int CS>
+__global__ void __launch_bounds__(256, 2)
+    wgrad_small3_kernel(const TS* __restrict__ s, int lds, const TW* __restrict__ wd, int ldw, int Cw, int N, int H, int W,
+                        int64_t pix_per_block, float* __restrict__ dw) {
+  PHS_PDL_PROLOGUE();
+  extern __shared__ float red[];  // [nvec * CS][72]
+  const int nvec = Cw / 8;
+  const int pairs = nvec * CS;
+  const int PL = blockDim.x / pairs;
+  const int pr = threadIdx.x % pairs, lp = threadIdx.x / pairs;
+  const int cv = pr % nvec, cs = pr / nvec;
+  for (int i = threadIdx.x; i < pairs * 72; i += blockDim.x) red[i] = 0.f;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[t][o] = 0.f;
+  const int64_t M = (int64_t)N * H * W;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < M ? p0 + pix_per_block : M;
+  const bool active = lp < PL && p0 < p1;
+  if (active) {
+    // each pixel lane owns a contiguous sub-range: (h, w) are tracked incrementally, no divisions in the loop
+    const int64_t chunk = (pix_per_block + PL - 1) / PL;
+    int64_t p = p0 + (int64_t)lp * chunk;
+    const int64_t pe = p + chunk < p1 ? p + chunk : p1;
+    int wq = (int)(p % W);
+    int hq = (int)((p / W) % H);
+    for (; p < pe; p += 2) {
+      Raw8<TW> raw[2];
+      float sv[2][9];
+      int ww = wq, hh = hq;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t q = p + u;
+        const bool in = q < pe;
+        const int64_t qc = in ? q : pe - 1;
+        raw[u].load(wd + qc * ldw + cv * 8);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dh = t / 3 - 1, dx = t % 3 - 1;
+          const int h2 = hh + dh, w2 = ww + dx;
+          const bool ok = in && h2 >= 0 && h2 < H && w2 >= 0 && w2 < W;
+          sv[u][t] = ok ? ldf<TS>(s + (q + (int64_t)dh * W + dx) * lds + cs) : 0.f;
+        }
+        if (++ww == W) {
+          ww = 0;
+          if (++hh == H) hh = 0;
+        }
+      }
+      wq = ww;
+      hq = hh;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float v[8];
+        raw[u].unpack(v);
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[t][o] = fmaf(sv[u][t], v[o], acc[t][o]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int l = 0; l < PL; ++l) {          // one pixel lane at a time: every (pair, tap, channel) slot has one writer
+    if (active && lp == l) {
+      float* d = red + (size_t)pr * 72;
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) d[t * 8 + o] += acc[t][o];
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < pairs * 72; i += blockDim.x) {
+    const int o = i & 7, t = (i >> 3) % 9, pr2 = i / 72;
+    const int cv2 = pr2 % nvec, cs2 = pr2 / nvec;
+    atomicAdd(dw + ((size_t)t * CS + cs2) * Cw + cv2 * 8 + o, red[i]);       // [tap][ci = small][co = wide]
+  }
+}
+
 // ---- filter gradient of a 1x1 head (wide x, NS <= 8 output channels): dW[ci][co] = sum_p x[p][ci] * dy[p][co] -------
 // thread <-> (8-channel vector of x, pixel lane) and ALL output channels: the 16-byte x load is shared by NS FMAs x 8.
 // (round 2, ncu: 128x128 128->2 at 1.9 TB/s with four loads per thread outstanding and 592 blocks on 444 resident slots:
@@ -608,6 +697,29 @@ int small_wgrad_try(const phs_tensor* x, const phs_tensor* dy, float* dw, int ks
 #undef LAUNCH_WH
     int rc = phs_check_launch("wgrad_head_kernel");
     return rc ? rc : 1;
+  }
+  if (small_is_x && ksize == 3 && (s->C == 1 || s->C == 2) && s->C * (wd->C / 8) <= 128 && !getenv("PHS_NO_WGRAD_SMALL3")) {
+    // all nine taps per thread (wgrad_small3_kernel)
+    const int pairs3 = s->C * (wd->C / 8);
+    const int PL = 256 / pairs3;
+    int64_t splits = 148 * 2;
+    if (splits > (M + PL * 8 - 1) / (PL * 8)) splits = (M + PL * 8 - 1) / (PL * 8);     // >= 8 pixels per pixel lane
+    if (splits < 1) splits = 1;
+    const int64_t ppb = (M + splits - 1) / splits;
+    splits = (M + ppb - 1) / ppb;
+    const size_t smem3 = (size_t)pairs3 * 72 * sizeof(float);
+#define LAUNCH_W3(TS, TW)                                                                                              \
+  do {                                                                                                                 \
+    if (s->C == 1) phs_launch(wgrad_small3_kernel<TS, TW, 1>, (unsigned)splits, 256, smem3, st, (const TS*)s->ptr, s->ld, (const TW*)wd->ptr, wd->ld, wd->C, x->N, x->H, x->W, ppb, dw); \
+    else phs_launch(wgrad_small3_kernel<TS, TW, 2>, (unsigned)splits, 256, smem3, st, (const TS*)s->ptr, s->ld, (const TW*)wd->ptr, wd->ld, wd->C, x->N, x->H, x->W, ppb, dw); \
+  } while (0)
+    if (s->dtype == PHS_F32 && wd->dtype == PHS_F32) LAUNCH_W3(float, float);
+    else if (s->dtype == PHS_F32) LAUNCH_W3(float, bf16);
+    else if (wd->dtype == PHS_F32) LAUNCH_W3(bf16, float);
+    else LAUNCH_W3(bf16, bf16);
+#undef LAUNCH_W3
+    int rc3 = phs_check_launch("wgrad_small3_kernel");
+    return rc3 ? rc3 : 1;
   }
   const int taps = ksize * ksize;
   const int pairs = taps * s->C * (wd->C / 8);

@@ -98,6 +98,14 @@ def test_conv_mixed_dtypes(call, lib, oracle):
     call('phs_conv2d', call.T(cu(z)), cu(wz), cu(bz), call.T(yz), 3, 0, 0, lib.IMPL_SIMT)
     refz = oracle.conv2d_same(z.double(), wz.double(), bz.double())
     close(yz, refz, rtol=2 ** -8, what='f32 in, bf16 out (z input)')
+    # ... and its filter gradient: f32 z, bf16 dy (all nine taps per thread, wgrad_small3_kernel), against the same sum in fp64
+    gy = torch.randn(3, 16, 16, 64, generator=g).to(torch.bfloat16)
+    zp = torch.nn.functional.pad(z.double(), (0, 0, 1, 1, 1, 1))
+    gw_ref = torch.stack([torch.einsum('nhwc,nhwo->co', zp[:, kh:kh + 16, kw:kw + 16], gy.double())
+                          for kh in range(3) for kw in range(3)]).reshape(3, 3, 2, 64)
+    gwz = torch.zeros(3, 3, 2, 64, device='cuda')
+    call('phs_conv2d_wgrad', call.T(cu(z)), call.T(gy.cuda()), gwz, None, 3, 0, lib.IMPL_SIMT)
+    close(gwz, gw_ref, rtol=5e-5, what='wgrad of the z-input convolution (f32 x, bf16 dy)')
 
 
 def test_conv_argument_errors(call, lib):
