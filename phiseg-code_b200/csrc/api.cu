@@ -23,6 +23,16 @@ int phs_pdl_enabled() {
   return v;
 }
 
+// PHS_PDL_TC=1: tensor-memory kernels are launched early too (off by default, see PHS_PDL_WAIT in common.cuh)
+int phs_pdl_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PHS_PDL_TC");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 int phs_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -37,6 +37,19 @@ int phs_pdl_enabled();
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
   } while (0)
 
+// Kernels that allocate TENSOR MEMORY split the prologue: PHS_PDL_WAIT() where PHS_PDL_PROLOGUE() would stand, and
+// PHS_PDL_TRIGGER() only after the CTA holds its tensor memory (behind the barrier that publishes the TMEM base address).
+// tcgen05.alloc blocks without a time limit when the SM's 512 columns are taken, and launch_dependents counts per CTA as soon
+// as ONE thread issues it: with the trigger in front of the allocation, the other warps of a CTA released the successor
+// kernel while its MMA warp was still waiting for columns; the successor's CTAs - resident early, allocating in their own
+// prologue, then parked in griddepcontrol.wait until this kernel completes - could take exactly those columns: a cycle
+// that never resolves (round 2: two training runs in ~20 stalled for minutes inside a step; all other waits in these
+// kernels are bounded).  For the same reason tcgen05 kernels are not launched early THEMSELVES (phs_launch_tc: no
+// programmatic attribute unless PHS_PDL_TC=1): a CTA that holds tensor memory never sits in griddepcontrol.wait.
+#define PHS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PHS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+int phs_pdl_tc_enabled();
+
 template <typename... KArgs, typename... Args>
 static inline void phs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -49,6 +62,22 @@ static inline void phs_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = phs_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// tensor-memory kernels (see PHS_PDL_WAIT above): the programmatic attribute only on request
+template <typename... KArgs, typename... Args>
+static inline void phs_launch_tc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (phs_pdl_enabled() && phs_pdl_tc_enabled()) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -69,7 +98,7 @@ static inline void phs_launch_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = phs_pdl_enabled() ? 2 : 1;
+  cfg.numAttrs = (phs_pdl_enabled() && phs_pdl_tc_enabled()) ? 2 : 1;      // (only tensor-memory kernels run as clusters)
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -217,7 +217,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (PAIR) tmem_alloc_pair(smem_u32(&tmem_base_s), p.tmem_cols);
     else tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
   }
-  PHS_PDL_PROLOGUE();     // everything above touches only shared / tensor memory and kernel parameters
+  PHS_PDL_WAIT();     // everything above touches only shared / tensor memory and kernel parameters
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
   if (POST) {
     // (scale, shift) of every output channel: the expressions of norm_finalize_kernel (inference) + norm_act_fwd_kernel
@@ -232,6 +232,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  PHS_PDL_TRIGGER();      // this CTA holds its tensor memory: the successor kernel may be scheduled now
   stamp();
 
   // contiguous tile range of this CTA (pair: of the pair, which walks it two tiles at a time - rank r takes tiles
@@ -926,20 +927,20 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
     static bool attr = false;                                                                             \
     if ((rc = allow_big_smem(conv_halo_kernel<BKV, PAIRV, SWV, false>, &attr))) return rc;                \
     if (PAIRV) phs_launch_cluster2(conv_halo_kernel<BKV, PAIRV, SWV, false>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
-    else phs_launch(conv_halo_kernel<BKV, PAIRV, SWV, false>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
+    else phs_launch_tc(conv_halo_kernel<BKV, PAIRV, SWV, false>, grid, SWV ? 320 : 192, smem, st, tmA, tmB, tmY, p); \
   } while (0)
 #define PHS_HALO_LAUNCH_PRE(BKV)                                                                          \
   do {                                                                                                    \
     static bool attr = false;                                                                             \
     if ((rc = allow_big_smem(conv_halo_kernel<BKV, false, false, true>, &attr))) return rc;               \
-    phs_launch(conv_halo_kernel<BKV, false, false, true>, grid, 256, smem, st, tmA, tmB, tmY, p);         \
+    phs_launch_tc(conv_halo_kernel<BKV, false, false, true>, grid, 256, smem, st, tmA, tmB, tmY, p);         \
   } while (0)
 #define PHS_HALO_LAUNCH_POST(BKV, PAIRV)                                                                  \
   do {                                                                                                    \
     static bool attr = false;                                                                             \
     if ((rc = allow_big_smem(conv_halo_kernel<BKV, PAIRV, false, false, true>, &attr))) return rc;        \
     if (PAIRV) phs_launch_cluster2(conv_halo_kernel<BKV, PAIRV, false, false, true>, grid, 192, smem, st, tmA, tmB, tmY, p); \
-    else phs_launch(conv_halo_kernel<BKV, PAIRV, false, false, true>, grid, 192, smem, st, tmA, tmB, tmY, p); \
+    else phs_launch_tc(conv_halo_kernel<BKV, PAIRV, false, false, true>, grid, 192, smem, st, tmA, tmB, tmY, p); \
   } while (0)
   if (post) {
     if (BK == 64) { if (pair) PHS_HALO_LAUNCH_POST(64, true); else PHS_HALO_LAUNCH_POST(64, false); }

@@ -244,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), 512);
-  PHS_PDL_PROLOGUE();
+  PHS_PDL_WAIT();
   for (int c = threadIdx.x; c < 256; c += blockDim.x) bias_s[c] = (p.bias && c < p.Cout) ? p.bias[c] : 0.f;
   if (p.post_on) {
     for (int c = threadIdx.x; c < p.Cout; c += blockDim.x)
@@ -255,6 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  PHS_PDL_TRIGGER();      // this CTA holds its tensor memory: the successor kernel may be scheduled now
   const int kiters = p.taps * p.kchunks;
 
   // lean, warp-uniform issue loops: ring index / phase are counters, descriptors advance by adds (see conv_halo.cu)
@@ -405,11 +406,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
-  PHS_PDL_PROLOGUE();
+  PHS_PDL_WAIT();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  PHS_PDL_TRIGGER();      // this CTA holds its tensor memory: the successor kernel may be scheduled now
 
   const int stages = p.stages;
   if (warp == W_PROD) {
@@ -648,11 +650,11 @@ static int conv2d_tc_impl(const phs_tensor* x, const void* w, const float* bias,
   if (BK == 64) {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_tc_kernel<64>, &attr))) return rc;
-    phs_launch(conv_tc_kernel<64>, grid, 192, smem, st, tmA, tmB, p);
+    phs_launch_tc(conv_tc_kernel<64>, grid, 192, smem, st, tmA, tmB, p);
   } else {
     static bool attr = false;
     if ((rc = allow_big_smem(conv_tc_kernel<32>, &attr))) return rc;
-    phs_launch(conv_tc_kernel<32>, grid, 192, smem, st, tmA, tmB, p);
+    phs_launch_tc(conv_tc_kernel<32>, grid, 192, smem, st, tmA, tmB, p);
   }
   return phs_check_launch("conv_tc_kernel");
 }
@@ -713,7 +715,7 @@ int conv2d_wgrad_tc(const phs_tensor* x, const phs_tensor* dy, float* dw, float*
   static bool attr = false;
   if ((rc = allow_big_smem(wgrad_tc_kernel, &attr))) return rc;
   const int smem = stages * stage_bytes + 1024;
-  phs_launch(wgrad_tc_kernel, dim3(splits, items), 192, smem, st, tmX, tmDY, p);
+  phs_launch_tc(wgrad_tc_kernel, dim3(splits, items), 192, smem, st, tmX, tmDY, p);
   rc = phs_check_launch("wgrad_tc_kernel");
   if (rc) return rc;
   return db ? bias_grad_tc(dy, db, st) : 0;

@@ -93,11 +93,12 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(&tmem_base_s), p.tmem_cols);
-  PHS_PDL_PROLOGUE();
+  PHS_PDL_WAIT();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  PHS_PDL_TRIGGER();      // this CTA holds its tensor memory: the successor kernel may be scheduled now
 
   // lean, warp-uniform issue loops (see conv_halo.cu): counters instead of divisions, descriptors advanced by adds
   const int stages = p.stages, a_boxes = p.a_boxes, nslabB = p.nslabB, n_acc = p.n_acc, nb = p.nb, nkh = p.nkh;
@@ -288,7 +289,7 @@ static int wgrad_halo_impl(const phs_tensor* x, const phs_tensor* dy, float* dw,
   static bool attr = false;
   if ((rc = allow_big_smem(wgrad_halo_kernel, &attr))) return rc;
   const int smem = stages * stage_bytes + 2048;
-  phs_launch(wgrad_halo_kernel, dim3(items, splits), 192, smem, st, tmX, tmDY, p);
+  phs_launch_tc(wgrad_halo_kernel, dim3(items, splits), 192, smem, st, tmX, tmDY, p);
   return phs_check_launch("wgrad_halo_kernel");
 }
 

@@ -71,7 +71,7 @@ def test_every_programmatically_launched_kernel_waits_for_its_predecessor():
     src = {f: open(os.path.join(csrc, f)).read() for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))}
     launched = set()
     for txt in src.values():
-        for m in re.finditer(r'phs_launch\(\s*([A-Za-z_]\w*)', txt):
+        for m in re.finditer(r'phs_launch(?:_tc|_cluster2)?\(\s*([A-Za-z_]\w*)', txt):
             launched.add(m.group(1))
     launched -= {'kernel', 'void'}      # the helper's own definition in common.cuh
     assert len(launched) >= 20
@@ -88,4 +88,13 @@ def test_every_programmatically_launched_kernel_waits_for_its_predecessor():
                 body = txt[i:j]
                 break
         assert body is not None, 'kernel %s not found' % k
-        assert 'PHS_PDL_PROLOGUE()' in body, 'kernel %s is launched with programmatic serialization but never waits' % k
+        if 'tmem_alloc' in body:
+            # tensor-memory kernels: wait in the prologue, but release the successor only once the CTA HOLDS its tensor memory
+            # (behind the barrier that follows the allocation) - a trigger in front of a blocking tcgen05.alloc lets the
+            # successor's early CTAs take the columns this kernel is waiting for (common.cuh, PHS_PDL_WAIT)
+            assert 'PHS_PDL_PROLOGUE()' not in body, k
+            w, a, t = body.index('PHS_PDL_WAIT()'), body.index('tmem_alloc'), body.index('PHS_PDL_TRIGGER()')
+            sync = min(i for i in (body.find('__syncthreads()', a), body.find('cluster_sync_all()', a)) if i >= 0)
+            assert a < sync < t and w < t, 'kernel %s triggers its successor before it holds tensor memory' % k
+        else:
+            assert 'PHS_PDL_PROLOGUE()' in body, 'kernel %s is launched with programmatic serialization but never waits' % k
