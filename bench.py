@@ -124,6 +124,45 @@ def run_cpu_oracle(steps, warmup, batch=CPU_BATCH, size=128):
     return batch * steps / dt, dt / steps, cores
 
 
+# the conservative launch configuration (= the library defaults since the end of round 2; spelled out so that a retry does
+# not inherit opt-in switches from the caller's environment)
+SAFE_LAUNCH_ENV = {'PHS_PDL': '0', 'PHS_HALO_PAIR': '0'}
+
+
+def supervise(argv, attempt_timeout=None):
+    """Run the b200 arm in a child process; on a stall / failure kill it and retry once with SAFE_LAUNCH_ENV.  Prints the
+    child's JSON line (with config.launch_config naming the configuration that produced it) and returns its exit code."""
+    import subprocess
+    timeout = float(attempt_timeout or os.environ.get('BENCH_ATTEMPT_TIMEOUT', '420'))
+    attempts = [({}, 'library defaults' + ''.join(' %s=%s' % (k, os.environ[k]) for k in ('PHS_PDL', 'PHS_HALO_PAIR') if k in os.environ)),
+                (SAFE_LAUNCH_ENV, 'retry after a stalled / failed first attempt: '
+                                  + ' '.join('%s=%s' % kv for kv in sorted(SAFE_LAUNCH_ENV.items())))]
+    last_rc = 1
+    for env_over, label in attempts:
+        env = dict(os.environ, BENCH_CHILD='1')
+        env.update(env_over)
+        p = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + list(argv), env=env, stdout=subprocess.PIPE, text=True)
+        try:
+            out, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+            sys.stderr.write('bench.py: attempt [%s] did not finish within %.0f s and was killed\n' % (label, timeout))
+            continue
+        last_rc = p.returncode
+        lines = [l for l in out.splitlines() if l.startswith('{')]
+        if p.returncode == 0 and lines:
+            try:
+                line = json.loads(lines[-1])
+                line.setdefault('config', {})['launch_config'] = label
+                print(json.dumps(line))
+            except ValueError:
+                print(lines[-1])
+            return 0
+        sys.stderr.write('bench.py: attempt [%s] failed (exit code %s)\n' % (label, p.returncode))
+    return last_rc or 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -160,10 +199,24 @@ def main():
         print(json.dumps(line))
         return 0
 
-    # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 900) dumps its Python stacks and exits -
-    # a stuck launch must end as a failed run with a traceback, never as a box that hangs until an outer limit kills it
+    # Supervision (single-GPU runs): the measurement runs in a child process; if it stalls or fails it is killed and the run
+    # is repeated ONCE in the conservative launch configuration (no programmatic dependent launch, no CTA pairs), which is
+    # then named in config.launch_config.  Two training runs at the end of round 2 stalled inside a step (DESIGN.md
+    # section 2); the cause was hardened by construction but could not be re-measured, so the bench must not depend on it.
+    if world == 1 and os.environ.get('BENCH_CHILD') is None and os.environ.get('BENCH_SUPERVISE', '1') != '0':
+        return supervise(sys.argv[1:])
+    if os.environ.get('BENCH_SELFTEST') == 'stall-then-ok':
+        # test hook of the supervisor (tests/test_bench_contract.py): the default configuration stalls, the conservative
+        # one answers - no GPU involved
+        if os.environ.get('PHS_PDL') != '0':
+            time.sleep(3600)
+        print(json.dumps({'metric': metric, 'value': 1.0, 'config': {'workload': 'selftest'}}))
+        return 0
+    # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 300; a full run takes well under a minute
+    # once torch is imported) dumps its Python stacks and exits - a stuck launch must end as a failed run with a traceback,
+    # never as a box that hangs until an outer limit kills it
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '900')), repeat=False, exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '300')), repeat=False, exit=True)
 
     import numpy as np
     import torch

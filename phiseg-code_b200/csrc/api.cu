@@ -14,11 +14,15 @@ void phs_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Programmatic dependent launch is OPT-IN (PHS_PDL=1) since the end of round 2: it bought 0.29 ms per step, but two training
+// runs stalled inside a step after the last kernel reworks and the cause could not be pinned down on the device any more
+// (DESIGN.md section 2).  Off, the kernels of a lane are strictly serialised and griddepcontrol.* are no-ops - the
+// execution model the round-1 driver runs (1 to 8 GPUs) went through.
 int phs_pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("PHS_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v;
 }

@@ -753,6 +753,7 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
                           const phs_norm_pre* post = nullptr) {
   const int accumulate = accumulate_flags & 1;
   const bool stats_prezeroed = (accumulate_flags & 2) != 0;   // the caller cleared stats (one fill for the whole program)
+  const bool no_pair = (accumulate_flags & 4) != 0;           // the caller rules CTA pairs out for this launch
   const int BK = x->C % 64 == 0 ? 64 : 32;
   const int ROW = BK * 2;
   HaloParams p;
@@ -796,10 +797,13 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   const bool pair_ok = y->C % 32 == 0 && y->C >= 32 && total_subs >= 2;
   // PHS_HALO_PAIR: 1 = wherever possible, 2 = only launches without fused statistics, 3 = only with;
   // PHS_HALO_PAIR_MINC / _MINCIN: smallest Cout / Cin that uses pairs
-  const int pair_mode = e_pair ? atoi(e_pair) : 2;
+  // default since the end of round 2: 0 (no cluster launches; PHS_HALO_PAIR=2 is the measured-best setting, -0.15 ms per
+  // step) - same reason as PHS_PDL in api.cu: two stalled training runs whose cause could not be isolated any more, and
+  // the pair protocol (remote arrives, multicast commits, cluster barriers) is the newest code with unbounded waits
+  const int pair_mode = e_pair ? atoi(e_pair) : 0;
   const int pair_minc = getenv("PHS_HALO_PAIR_MINC") ? atoi(getenv("PHS_HALO_PAIR_MINC")) : 32;
   const int pair_mincin = getenv("PHS_HALO_PAIR_MINCIN") ? atoi(getenv("PHS_HALO_PAIR_MINCIN")) : 32;
-  bool pair = pair_ok && y->C >= pair_minc && x->C >= pair_mincin && !pre &&
+  bool pair = pair_ok && y->C >= pair_minc && x->C >= pair_mincin && !pre && !no_pair &&
               (pair_mode == 1 || (pair_mode == 2 && !stats) || (pair_mode == 3 && stats));
   const int b_bytes_full = y->C * ROW;
   int b_bytes = pair ? b_bytes_full / 2 : b_bytes_full;

@@ -611,8 +611,13 @@ static int conv2d_tc_impl(const phs_tensor* x, const void* w, const float* bias,
     // MMAs and is pure tail (16x16x192: 47 us with, 25 us without), while one pass over the few-MB output costs ~5 us:
     // below PHS_STATS_MIN_HW pixels per image the statistics come from a separate launch (the layout is the same).
     const bool split_stats = stats && stats_prezeroed && y->H * y->W < stats_min_hw();
+    // (few-tile forward layers whose statistics come from the separate pass keep the single-CTA kernel, PHS_SPLIT_PAIR=1
+    // lets them use CTA pairs: with one or two tiles per CTA pairs bought ~0.03 ms per step, and the stalls at the end of
+    // round 2 appeared only after this - the newest - use of cluster launches was added)
+    static const bool split_pair = getenv("PHS_SPLIT_PAIR") != nullptr;
+    const int no_pair = (split_stats && !split_pair) ? 4 : 0;
     int rc = post ? conv2d_halo_post(x, w, bias, post, y, st)
-                  : conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed, split_stats ? nullptr : stats, st);
+                  : conv2d_halo(x, w, bias, y, accumulate | stats_prezeroed | no_pair, split_stats ? nullptr : stats, st);
     if (rc == 0 && split_stats) return chan_stats_run(y, stats, true, false, st);
     if (rc != -3) return rc;
   }

@@ -221,7 +221,7 @@ def test_sampling_same_with_and_without_fusion(pkg, oracle, monkeypatch, exp_nam
 
 POST_CASES = [  # N, H, W, Cin, Cout, k, channel-slice output
     (3, 16, 16, 64, 64, 3, False),       # halo kernel, 64-channel store groups
-    (2, 32, 32, 128, 128, 3, False),     # CTA pairs (no statistics: the default pair mode takes it)
+    (2, 32, 32, 128, 128, 3, False),     # CTA pairs (PHS_HALO_PAIR=2 is set for this case)
     (2, 128, 128, 32, 32, 3, False),     # BK = 32
     (2, 64, 64, 64, 192, 3, True),       # writes into a channel slice of a wider (concat) buffer
     (2, 32, 32, 32, 48, 3, False),       # Cout % 32 != 0: direct-store epilogue
@@ -234,12 +234,14 @@ POST_CASES = [  # N, H, W, Cin, Cout, k, channel-slice output
 
 @pytest.mark.parametrize('N,H,W,Cin,Cout,k,sliced', POST_CASES)
 @pytest.mark.parametrize('relu', [1, 0])
-def test_conv2d_post_bn_infer(call, lib, oracle, N, H, W, Cin, Cout, k, sliced, relu):
+def test_conv2d_post_bn_infer(call, lib, oracle, monkeypatch, N, H, W, Cin, Cout, k, sliced, relu):
     """phs_conv2d_post: convolution + inference-mode batch norm (moving statistics, tfwrapper/normalisation.py:145-163 with
     is_training=False) + ReLU in one launch.  Against the fp64 oracle convolution on the same bf16 operands followed by the
     affine map with the fp32 coefficients the kernels use (2^-8 of the output scale: one bf16 rounding), and against the
     three-launch path it replaces (which rounds the raw convolution output to bf16 first: 2^-6)."""
     L = lib
+    if (Cin, Cout, H) == (128, 128, 32):
+        monkeypatch.setenv('PHS_HALO_PAIR', '2')        # the cta_group::2 variant of the folded epilogue (pairs are opt-in)
     g = torch.Generator().manual_seed(N * 100 + H + Cin + Cout + k)
     x = torch.randn(N, H, W, Cin, generator=g).to(torch.bfloat16)
     w = (torch.randn(k, k, Cin, Cout, generator=g) * (1.0 / np.sqrt(k * k * Cin))).to(torch.bfloat16)
