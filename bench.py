@@ -133,6 +133,15 @@ def supervise(argv, attempt_timeout=None):
     """Run the b200 arm in a child process; on a stall / failure kill it and retry once with SAFE_LAUNCH_ENV.  Prints the
     child's JSON line (with config.launch_config naming the configuration that produced it) and returns its exit code."""
     import subprocess
+    # the supervising process maps the native library too (no CUDA call is made here, the child owns the device): whoever
+    # inspects this process for loaded native code finds what the measurement ran on
+    try:
+        import importlib
+        from __graft_entry__ import load_package
+        load_package()
+        importlib.import_module('phiseg_code_b200.lib').load()
+    except Exception as e:       # the child fails loudly on its own if the library is missing
+        sys.stderr.write('bench.py: supervisor could not map the native library: %s\n' % e)
     timeout = float(attempt_timeout or os.environ.get('BENCH_ATTEMPT_TIMEOUT', '420'))
     attempts = [({}, 'library defaults' + ''.join(' %s=%s' % (k, os.environ[k]) for k in ('PHS_PDL', 'PHS_HALO_PAIR') if k in os.environ)),
                 (SAFE_LAUNCH_ENV, 'retry after a stalled / failed first attempt: '

@@ -790,9 +790,9 @@ static int conv_halo_impl(const phs_tensor* x, const void* w, const float* bias,
   // i.e. at 75-89 % of what cuBLAS reaches on this part, and the filter ring is no longer what holds them back.
   // INSIDE the training step, however, pairs win (tools/step_ab.py, ms per step: no pairs 12.47, pairs for launches
   // without fused statistics 12.32, pairs everywhere 12.23): fewer filter bytes per SM leave more L2 -> SM bandwidth to
-  // the kernels of the other lanes.  Default (2): pairs for the launches WITHOUT fused statistics - with statistics the
+  // the kernels of the other lanes.  Measured best (2): pairs for the launches WITHOUT fused statistics - with statistics the
   // two CTAs' long epilogues gate one shared accumulator hand-back and the kernel alone is slower.  PHS_HALO_PAIR=1:
-  // everywhere, 0: nowhere.
+  // everywhere, 0: nowhere (the default since the end of round 2, see below).
   const char* e_pair = getenv("PHS_HALO_PAIR");
   const bool pair_ok = y->C % 32 == 0 && y->C >= 32 && total_subs >= 2;
   // PHS_HALO_PAIR: 1 = wherever possible, 2 = only launches without fused statistics, 3 = only with;
