@@ -142,7 +142,7 @@ def supervise(argv, attempt_timeout=None):
         importlib.import_module('phiseg_code_b200.lib').load()
     except Exception as e:       # the child fails loudly on its own if the library is missing
         sys.stderr.write('bench.py: supervisor could not map the native library: %s\n' % e)
-    timeout = float(attempt_timeout or os.environ.get('BENCH_ATTEMPT_TIMEOUT', '420'))
+    timeout = float(attempt_timeout or os.environ.get('BENCH_ATTEMPT_TIMEOUT', '260'))
     attempts = [({}, 'library defaults' + ''.join(' %s=%s' % (k, os.environ[k]) for k in ('PHS_PDL', 'PHS_HALO_PAIR') if k in os.environ)),
                 (SAFE_LAUNCH_ENV, 'retry after a stalled / failed first attempt: '
                                   + ' '.join('%s=%s' % kv for kv in sorted(SAFE_LAUNCH_ENV.items())))]
@@ -221,11 +221,11 @@ def main():
             time.sleep(3600)
         print(json.dumps({'metric': metric, 'value': 1.0, 'config': {'workload': 'selftest'}}))
         return 0
-    # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 300; a full run takes well under a minute
+    # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 200; a full run takes well under a minute
     # once torch is imported) dumps its Python stacks and exits - a stuck launch must end as a failed run with a traceback,
     # never as a box that hangs until an outer limit kills it
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '300')), repeat=False, exit=True)
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '200')), repeat=False, exit=True)
 
     import numpy as np
     import torch
