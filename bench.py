@@ -224,8 +224,6 @@ def main():
     # watchdog: a run that has not finished after BENCH_WATCHDOG seconds (default 200; a full run takes well under a minute
     # once torch is imported) dumps its Python stacks and exits - a stuck launch must end as a failed run with a traceback,
     # never as a box that hangs until an outer limit kills it
-    import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '200')), repeat=False, exit=True)
 
     import numpy as np
     import torch
@@ -236,6 +234,8 @@ def main():
     pm = importlib.import_module('phiseg_code_b200.phiseg.phiseg_model')
     ex = importlib.import_module('phiseg_code_b200.phiseg.experiments')
     rank, world, local = parallel.init_from_env()
+    import faulthandler      # (armed after the imports and the rendezvous: a fresh box can take a minute to page torch in)
+    faulthandler.dump_traceback_later(int(os.environ.get('BENCH_WATCHDOG', '200')), repeat=False, exit=True)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
 
