@@ -41,10 +41,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU.
+// Bounded wait: a pipeline bug must end in a trap (reported as a CUDA error), never in a hung GPU.  The bound is TIME
+// (4 s on %globaltimer, looked at every 1024 unsuccessful polls), not a poll count: mbarrier.try_wait may suspend the
+// thread for a system-dependent interval per call, so 2^26 polls - the round-1/2 bound - can be many minutes, which is
+// indistinguishable from a hang for whoever waits on the host (end of round 2: two stalled runs).
+// No legitimate wait in these kernels lasts more than a few milliseconds.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (true) {
     asm volatile(
         "{\n"
@@ -56,7 +61,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 1023u) == 0) {
+      uint64_t t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
